@@ -1,0 +1,174 @@
+/*
+ * ucnerf_b200 - C ABI of the B200-native UC-NeRF forward-render hot path.
+ *
+ * Plain C: pointers, sizes and PODs only (no torch / ATen types).  All `const void*` / `void*`
+ * data pointers are DEVICE pointers unless the function name ends in `_host`.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Every entry point returns 0 on
+ * success and a non-zero code on failure; ucnerf_last_error() then returns a message (thread
+ * local).  Nothing is retained across calls except what lives inside a ucnerf_model handle.
+ *
+ * Reference interface each entry point replaces (paths under /root/reference/nerf/):
+ *   ucnerf_grid_encode_forward   <- grid_encode_forward   gridencoder/src/gridencoder.h:L12, gridencoder.cu:L448-471
+ *   ucnerf_grid_encode_backward  <- grid_encode_backward  gridencoder/src/gridencoder.h:L13, gridencoder.cu:L473-503
+ *   ucnerf_grad_total_variation  <- grad_total_variation  gridencoder/src/gridencoder.h:L15, gridencoder.cu:L639-645
+ *   ucnerf_model_* / ucnerf_render_rays[_host]
+ *                                <- Model.forward eval path internal/models.py:L97-324 (level loop,
+ *                                   stepfun.py resampling, render.py cast_rays / compute_alpha_weights /
+ *                                   volumetric_rendering, MLP.forward models.py:L514-685), called per chunk
+ *                                   from render_image models.py:L907-1007.
+ * The Python-side binding a reference maintainer would add is shown in INTEGRATION.md.
+ */
+#ifndef UCNERF_B200_H
+#define UCNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UCNERF_ABI_VERSION 1
+
+/* embeddings / outputs / grad dtype codes (reference: AT_DISPATCH_FLOATING_TYPES_AND_HALF) */
+#define UCNERF_F32 0
+#define UCNERF_F16 1
+#define UCNERF_F64 2
+
+#define UCNERF_MAX_GRID_LEVELS 16
+#define UCNERF_MAX_PROP_LEVELS 4
+
+int ucnerf_abi_version(void);
+const char* ucnerf_last_error(void);
+
+/* ---- gridencoder drop-in (gridencoder.h:L12-15). Argument meaning identical to the reference:
+ * inputs [B,D] f32 in [0,1]; embeddings [sum T,C]; offsets [L+1] int32; outputs [L,B,C] (caller
+ * allocated, embeddings dtype); S = log2(per_level_scale); H = base resolution; dy_dx [B,L*D*C] or
+ * NULL; gridtype 0 hash / 1 tiled; interp 0 linear / 1 smoothstep.  D in {2,3,4,5}, C in {1,2,4,8}
+ * else error (reference: std::runtime_error, gridencoder.cu:L381,L398). */
+int ucnerf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets,
+                               void* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                               uint32_t H, void* dy_dx, uint32_t gridtype, int align_corners,
+                               uint32_t interp, int dtype, void* stream);
+
+/* grad [L,B,C]; grad_embeddings [sum T,C] caller-zeroed, accumulated with atomics;
+ * dy_dx / grad_inputs [B,D] optional (both NULL or both set; grad_inputs is overwritten). */
+int ucnerf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                                const int32_t* offsets, void* grad_embeddings, uint32_t B, uint32_t D,
+                                uint32_t C, uint32_t L, float S, uint32_t H, const void* dy_dx,
+                                void* grad_inputs, uint32_t gridtype, int align_corners, uint32_t interp,
+                                int dtype, void* stream);
+
+/* inputs [B,D] (embeddings dtype, as in the reference), grad accumulated in place. */
+int ucnerf_grad_total_variation(const void* inputs, const void* embeddings, void* grad,
+                                const int32_t* offsets, float weight, uint32_t B, uint32_t D, uint32_t C,
+                                uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                int dtype, void* stream);
+
+/* ---- fused forward render (eval path, rand=False) ---- */
+
+/* One MLP's GridEncoder + density_layer (models.py:L425-441).  Pointers are device pointers to the
+ * tensors of the reference state_dict, in their native layouts (nn.Linear weight = [out,in]). */
+typedef struct ucnerf_mlp_desc {
+    const float* embeddings;      /* <prefix>.encoder.embeddings [sum T, C] (NOT copied: read at render time) */
+    const int32_t* offsets_host;  /* <prefix>.encoder.offsets  [L+1]  HOST pointer (copied)             */
+    const int32_t* grid_sizes_host; /* <prefix>.encoder.grid_sizes [L] HOST pointer (copied)             */
+    int32_t grid_levels;          /* L */
+    int32_t level_dim;            /* C (must be 4 on the fused path)                                     */
+    int32_t base_resolution;      /* H */
+    float log2_per_level_scale;   /* S */
+    const float* density0_w;      /* density_layer.0.weight [64, L*C] */
+    const float* density0_b;      /* density_layer.0.bias   [64]      */
+    const float* density2_w;      /* density_layer.2.weight [1 or bottleneck, 64] */
+    const float* density2_b;      /* density_layer.2.bias */
+} ucnerf_mlp_desc;
+
+typedef struct ucnerf_model_desc {
+    int32_t num_prop_levels;      /* Model.num_levels - 1 (>=1, <= UCNERF_MAX_PROP_LEVELS)  */
+    int32_t num_prop_samples;     /* Model.num_prop_samples                                  */
+    int32_t num_nerf_samples;     /* Model.num_nerf_samples                                  */
+    int32_t bottleneck_width;     /* MLP.bottleneck_width                                    */
+    int32_t net_width_viewdirs;   /* MLP.net_width_viewdirs (net_depth_viewdirs=2, skip_layer_dir=0 fixed) */
+    int32_t deg_view;             /* MLP.deg_view (4)                                        */
+    /* python floats of the reference are carried as doubles so derived fp32 constants round identically */
+    double dilation_multiplier;   /* Model.dilation_multiplier */
+    double dilation_bias;         /* Model.dilation_bias       */
+    double anneal_slope;          /* Model.anneal_slope        */
+    double resample_padding;      /* Model.resample_padding    */
+    double std_scale;             /* Model.std_scale           */
+    double bg_intensity;          /* Model.bg_intensity_range (min==max)                      */
+    double density_bias;          /* MLP.density_bias          */
+    double rgb_padding;           /* MLP.rgb_padding           */
+    ucnerf_mlp_desc prop[UCNERF_MAX_PROP_LEVELS];
+    ucnerf_mlp_desc nerf;
+    const float* view0_w;         /* nerf_mlp.lin_second_stage_0.weight [W, bottleneck+dir]   */
+    const float* view0_b;
+    const float* view1_w;         /* nerf_mlp.lin_second_stage_1.weight [W, W+bottleneck+dir] */
+    const float* view1_b;
+    const float* rgb_w;           /* nerf_mlp.rgb_layer.weight [3, W] */
+    const float* rgb_b;
+} ucnerf_model_desc;
+
+typedef struct ucnerf_model ucnerf_model;  /* opaque */
+
+/* Copies / re-lays-out the (small) MLP weights into library-owned device memory; keeps the
+ * embeddings pointers.  Call ucnerf_model_refresh after the source weights changed. */
+int ucnerf_model_create(const ucnerf_model_desc* desc, ucnerf_model** out);
+int ucnerf_model_refresh(ucnerf_model* m, const ucnerf_model_desc* desc, void* stream);
+int ucnerf_model_destroy(ucnerf_model* m);
+
+/* Ray batch (datasets.py:L386-476 keys).  All [N,3] / [N] f32, contiguous.  rand_vec is the
+ * cone-basis vector the reference draws with torch.randn_like(cam_dirs) (render.py:L140). */
+typedef struct ucnerf_rays {
+    const float* origins;
+    const float* directions;
+    const float* viewdirs;
+    const float* cam_dirs;
+    const float* radii;
+    const float* near;
+    const float* far;
+    const float* rand_vec;
+} ucnerf_rays;
+
+/* Outputs; any pointer may be NULL (not produced).  Level index l = 0..num_prop_levels (last = NeRF). */
+typedef struct ucnerf_outputs {
+    float* rgb;                   /* [N,3] final level */
+    float* depth;                 /* [N]   with the reference's acc<0.6 -> 300 override (render.py:L208,L213) */
+    float* depth_raw;             /* [N]   before that override */
+    float* acc;                   /* [N] */
+    float* distance_mean;         /* [N] */
+    float* distance_median;       /* [N] */
+    float* distance_percentile_5; /* [N] */
+    float* distance_percentile_95;/* [N] */
+    float* sdist[UCNERF_MAX_PROP_LEVELS + 1];   /* [N, S_l+1] normalised fenceposts of level l */
+    float* weights[UCNERF_MAX_PROP_LEVELS + 1]; /* [N, S_l] */
+    float* sample_rgb;            /* [N, S_nerf, 3] per-sample colours of the NeRF level */
+    float* sample_density;        /* [N, S_nerf] */
+    float* packed;                /* [N,12] (rgb[3], depth, acc, distance_mean, distance_median, distance_percentile_5,
+                                     distance_percentile_95, depth_raw, 0, 0): the one buffer the multi-GPU
+                                     tile all-gather moves */
+} ucnerf_outputs;
+
+/* Rays and outputs in device memory.  train_frac only enters through the anneal (models.py:L179-184). */
+int ucnerf_render_rays(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays* rays, double train_frac,
+                       const ucnerf_outputs* out, void* stream);
+
+/* Same, with HOST buffers (pinned or pageable): copies the ray batch in, renders, copies every
+ * non-NULL output back and synchronises the stream.  This is the end-to-end entry bench.py times. */
+int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays* rays_host, double train_frac,
+                            const ucnerf_outputs* out_host, void* stream);
+
+/* Number of kernels launched by this library in this process so far (bench.py's gpu_launches). */
+uint64_t ucnerf_launch_count(void);
+
+/* Tunables: "chunk_rays" (rays per internal chunk), "color_mlp" (0 = fp32 SIMT, 1 = tensor core). */
+int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value);
+
+/* Timing probe: when enabled (value != 0) ucnerf_render_rays records CUDA events around each kernel
+ * family and ucnerf_get_timing returns accumulated milliseconds: [resample, encode_prop, encode_nerf,
+ * color_mlp, composite]. */
+int ucnerf_get_timing(ucnerf_model* m, float* ms_out5, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UCNERF_B200_H */

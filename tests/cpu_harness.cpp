@@ -1,0 +1,106 @@
+// TEST INFRASTRUCTURE: instantiates the host+device algorithm templates of
+// ucnerf_b200/csrc/ray_algos.cuh with SerialExec so the not-gpu test-suite can check the device
+// logic (tie semantics of the resampler, cone sampling op order, hash indexing, compositing)
+// against the oracle in a container without a GPU.  Never linked into libucnerf_b200.so.
+// Build: g++ -O2 -ffp-contract=off -shared -fPIC -I/usr/local/cuda/include tests/cpu_harness.cpp
+#include <cstring>
+#include <vector>
+#include "../ucnerf_b200/csrc/ray_algos.cuh"
+
+using namespace ucnerf;
+
+extern "C" {
+
+void h_resample(int n_rays, int n_prev, const float* t_prev, const float* w_prev, int dilate, float dilation,
+                float anneal, float padding, int S, const float* u, float* out) {
+    std::vector<float> scratch(ResampleScratch::floats(n_prev, S));
+    SerialExec ex;
+    for (int r = 0; r < n_rays; ++r) {
+        ResampleScratch sc;
+        sc.carve(scratch.data(), n_prev, S);
+        resample_ray(ex, n_prev, t_prev ? t_prev + (size_t)r * (n_prev + 1) : nullptr,
+                     w_prev ? w_prev + (size_t)r * n_prev : nullptr, dilate != 0, dilation, anneal, padding, S, u, sc,
+                     out + (size_t)r * (S + 1));
+    }
+}
+
+// out_ray: [N, 10] = rgb[3], depth, depth_raw, acc, mean, median, p5, p95
+void h_composite(int n_rays, int S, const float* sdist, const float* density, const float* rgb, const float* dirs,
+                 const float* near, const float* far, float bg, int extras, float* out_w, float* out_ray) {
+    std::vector<float> scratch(CompositeScratch::floats(S));
+    SerialExec ex;
+    for (int r = 0; r < n_rays; ++r) {
+        CompositeScratch sc;
+        sc.carve(scratch.data(), S);
+        RayOutputs ro;
+        composite_ray(ex, S, sdist + (size_t)r * (S + 1), density + (size_t)r * S,
+                      rgb ? rgb + (size_t)r * S * 3 : nullptr, dirs + 3 * (size_t)r, near[r], far[r], bg, extras != 0, sc,
+                      out_w + (size_t)r * S, ro);
+        float* o = out_ray + 10 * (size_t)r;
+        o[0] = ro.rgb[0]; o[1] = ro.rgb[1]; o[2] = ro.rgb[2]; o[3] = ro.depth; o[4] = ro.depth_raw; o[5] = ro.acc;
+        o[6] = ro.dist_mean; o[7] = ro.dist_median; o[8] = ro.dist_p5; o[9] = ro.dist_p95;
+    }
+}
+
+// out_g [N,S,6,3] unit-cube coordinates, out_sigma [N,S,6]
+void h_cone_points(int n_rays, int S, const float* origins, const float* directions, const float* cam_dirs,
+                   const float* rand_vec, const float* radii, const float* near, const float* far, const float* sdist,
+                   float std_scale, float* out_g, float* out_sigma) {
+    ConeTable ct;
+    make_cone_table(ct);
+    for (int r = 0; r < n_rays; ++r) {
+        RayGeom rg;
+        make_ray_geom(rg, origins + 3 * r, directions + 3 * r, cam_dirs + 3 * r, rand_vec + 3 * r, radii[r], near[r], far[r]);
+        for (int s = 0; s < S; ++s) {
+            const float s0 = sdist[(size_t)r * (S + 1) + s], s1 = sdist[(size_t)r * (S + 1) + s + 1];
+            const float t0 = fa(fm(s0, rg.far), fm(fs(1.f, s0), rg.near));
+            const float t1 = fa(fm(s1, rg.far), fm(fs(1.f, s1), rg.near));
+            const ConeInterval ci = make_cone_interval(t0, t1);
+            for (int j = 0; j < 6; ++j) {
+                float g[3], sg;
+                cone_point(rg, ci, ct, j, s & 1, std_scale, g, sg);
+                float* og = out_g + (((size_t)r * S + s) * 6 + j) * 3;
+                og[0] = g[0]; og[1] = g[1]; og[2] = g[2];
+                out_sigma[((size_t)r * S + s) * 6 + j] = sg;
+            }
+        }
+    }
+}
+
+// fused-path hash lookup for B points: lv = L x {offset, hashmap_size, stride1, hashed, pow2_mask, scale_bits}
+void h_grid_features(int B, int L, const uint32_t* lvdesc, const float* table, const float* g, float* out) {
+    for (int b = 0; b < B; ++b) {
+        const float gg[3] = {g[3 * b], g[3 * b + 1], g[3 * b + 2]};
+        for (int l = 0; l < L; ++l) {
+            GridLevel lv;
+            lv.offset = lvdesc[6 * l]; lv.hashmap_size = lvdesc[6 * l + 1]; lv.stride1 = lvdesc[6 * l + 2];
+            lv.hashed = lvdesc[6 * l + 3]; lv.pow2_mask = lvdesc[6 * l + 4];
+            std::memcpy(&lv.scale, &lvdesc[6 * l + 5], 4);
+            const CellCoords c = cell_of(lv, gg);
+            float r[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t ii = level_index(lv, c.ix + (k & 1), c.iy + ((k >> 1) & 1), c.iz + ((k >> 2) & 1));
+                const float w = ((k & 1) ? c.fx : 1 - c.fx) * ((k & 2) ? c.fy : 1 - c.fy) * ((k & 4) ? c.fz : 1 - c.fz);
+                const float* v = table + 4 * ((size_t)lv.offset + ii);
+                for (int ch = 0; ch < 4; ++ch) r[ch] = fmaf(w, v[ch], r[ch]);
+            }
+            std::memcpy(out + ((size_t)b * L + l) * 4, r, 16);
+        }
+    }
+}
+}
+
+// debug variant: also returns the scratch arrays of the last ray processed (T, W(=probabilities), CW, C)
+extern "C" void h_resample_debug(int n_prev, const float* t_prev, const float* w_prev, int dilate, float dilation,
+                                 float anneal, float padding, int S, const float* u, float* out, float* T, float* W,
+                                 float* CW, float* C) {
+    std::vector<float> scratch(ResampleScratch::floats(n_prev, S));
+    SerialExec ex;
+    ResampleScratch sc;
+    sc.carve(scratch.data(), n_prev, S);
+    resample_ray(ex, n_prev, t_prev, w_prev, dilate != 0, dilation, anneal, padding, S, u, sc, out);
+    std::memcpy(T, sc.T, sizeof(float) * (3 * n_prev + 1));
+    std::memcpy(W, sc.W, sizeof(float) * (3 * n_prev + 1));
+    std::memcpy(CW, sc.CW, sizeof(float) * (3 * n_prev + 2));
+    std::memcpy(C, sc.C, sizeof(float) * S);
+}

@@ -1,0 +1,48 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/ucnerf_b200.h declares.
+No compute entry point is called here."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "ucnerf_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ucnerf_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 13
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ucnerf_b200.h but not exported"
+    from ucnerf_b200 import _lib
+    assert sorted(_lib.EXPORTS) == syms
+
+
+def test_abi_version_and_error_string(lib):
+    assert lib.ucnerf_abi_version() == 1
+    assert isinstance(lib.ucnerf_last_error(), bytes)
+
+
+def test_struct_sizes_match_header(lib):
+    """ctypes mirrors of the PODs must have the C layout (LP64)."""
+    from ucnerf_b200 import _lib
+    assert ctypes.sizeof(_lib.MlpDesc) == 3 * 8 + 4 * 4 + 4 * 8
+    assert ctypes.sizeof(_lib.ModelDesc) == 6 * 4 + 8 * 8 + 5 * ctypes.sizeof(_lib.MlpDesc) + 6 * 8
+    assert ctypes.sizeof(_lib.Rays) == 8 * 8
+    assert ctypes.sizeof(_lib.Outputs) == (8 + 5 + 5 + 3) * 8
+
+
+def test_argument_validation_without_gpu(lib):
+    """Bad D / C are rejected before any CUDA call (reference: std::runtime_error, gridencoder.cu:L381,L398)."""
+    rc = lib.ucnerf_grid_encode_forward(None, None, None, None, 0, 7, 4, 1, 1.0, 16, None, 0, 0, 0, 0, None)
+    assert rc != 0 and b"D must be" in lib.ucnerf_last_error()
+    rc = lib.ucnerf_grid_encode_forward(None, None, None, None, 0, 3, 3, 1, 1.0, 16, None, 0, 0, 0, 0, None)
+    assert rc != 0 and b"C must be" in lib.ucnerf_last_error()
+    rc = lib.ucnerf_grid_encode_forward(None, None, None, None, 0, 3, 4, 1, 1.0, 16, None, 0, 0, 0, 9, None)
+    assert rc != 0 and b"dtype" in lib.ucnerf_last_error()
+    # empty batch is a no-op success
+    assert lib.ucnerf_grid_encode_forward(None, None, None, None, 0, 3, 4, 1, 1.0, 16, None, 0, 0, 0, 0, None) == 0

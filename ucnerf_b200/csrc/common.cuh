@@ -1,0 +1,75 @@
+// Shared helpers for the ucnerf_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+
+namespace ucnerf {
+
+// ---- error plumbing for the C ABI ------------------------------------------------------------
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launch_count;
+
+#define UC_CUDA_OK(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::ucnerf::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+            return 2;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+#define UC_REQUIRE(cond, msg)                                                                     \
+    do {                                                                                          \
+        if (!(cond)) {                                                                            \
+            ::ucnerf::set_error(msg);                                                             \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+// every kernel launch of the library goes through this so gpu_launches can be reported
+#define UC_LAUNCH_CHECK()                                                                         \
+    do {                                                                                          \
+        ::ucnerf::g_launch_count.fetch_add(1, std::memory_order_relaxed);                         \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess) {                                                                  \
+            ::ucnerf::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e));  \
+            return 3;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+template <typename T>
+__host__ __device__ inline T div_up(T a, T b) {
+    return (a + b - 1) / b;
+}
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- 128-bit read-only gather (hash-table entries are read-only during a render) -------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ float4 ldg_f4(const float4* p) {
+    return __ldg(p);
+}
+#endif
+
+// ---- per-level geometry of a hash grid, precomputed on the host for the fused path -----------
+struct GridLevel {
+    uint32_t offset;        // entry offset of the level inside `embeddings`
+    uint32_t hashmap_size;  // entries in the level
+    uint32_t stride1;       // resolution + 1 (align_corners=False): dense index stride
+    uint32_t hashed;        // 1: XOR-prime hash, 0: dense index
+    uint32_t pow2_mask;     // hashmap_size-1 if power of two else 0 (then use %)
+    float scale;            // exp2f(l*S)*H - 1
+    float grid_size;        // python-side grid_sizes[l] (erf down-weighting), as float
+    float pad;
+};
+
+struct GridDesc {
+    const float4* table;  // C == 4 on the fused path
+    int num_levels;
+    GridLevel lv[16];
+};
+
+}  // namespace ucnerf

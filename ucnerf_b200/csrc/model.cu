@@ -1,0 +1,494 @@
+// Host side of the fused render path: model handle, weight re-layout, chunked launch sequence and
+// the HOST-buffer entry used for end-to-end timing.  C ABI in include/ucnerf_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/ucnerf_b200.h"
+#include "ray_march.cuh"
+
+namespace ucnerf {
+
+static thread_local std::string g_err;
+std::atomic<uint64_t> g_launch_count{0};
+void set_error(const std::string& msg) { g_err = msg; }
+
+// torch.linspace(start, end, steps) for float32 on CPU (ATen RangeFactoriesKernel): step in fp32,
+// symmetric evaluation from both ends, fused multiply-add (checked bit-exact in tests/test_host_logic.py).  stepfun.py:L203-204 deterministic_center u grid.
+static void torch_linspace_f32(float start, float end, int steps, float* out) {
+    if (steps == 1) { out[0] = start; return; }
+    const float step = (end - start) / (float)(steps - 1);
+    const int halfway = steps / 2;
+    for (int i = 0; i < steps; ++i) {
+        // the vectorised ATen kernel evaluates both branches with a fused multiply-add
+        out[i] = (i < halfway) ? std::fmaf(step, (float)i, start) : std::fmaf(-step, (float)(steps - i - 1), end);
+    }
+}
+
+static void deterministic_u(int S, float* out) {
+    const double pad = 1.0 / (2.0 * S);
+    const double eps = (double)kEps;
+    torch_linspace_f32((float)pad, (float)(1.0 - pad - eps), S, out);
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        UC_CUDA_OK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct LevelState {
+    GridDesc grid;
+    float g2[16];
+    int lmax = 0;
+    int S = 0;
+    DevBuf w1p, b1, w2, u;
+    float b2 = 0.f;
+    DevBuf sdist, weights;  // workspace when the caller does not ask for them
+};
+
+}  // namespace ucnerf
+
+using namespace ucnerf;
+
+struct ucnerf_model {
+    ucnerf_model_desc d;
+    std::vector<int32_t> offsets[UCNERF_MAX_PROP_LEVELS + 1], grid_sizes[UCNERF_MAX_PROP_LEVELS + 1];
+    int num_levels = 0;  // sampling levels = prop + 1
+    LevelState lv[UCNERF_MAX_PROP_LEVELS + 1];
+    ConeTable cone;
+    int np = 0;  // padded colour-MLP width
+    DevBuf w2t, b2, v0t, c0, v1t, c1, rt, r0;
+    DevBuf density, h1, rgb_s;
+    // host-entry staging
+    DevBuf stage_in, stage_out;
+    int64_t chunk_rays = 65536;
+    int color_mode = 0;
+    bool timing = false;
+    float ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::mutex mu;
+};
+
+namespace ucnerf {
+
+static int fetch_host(std::vector<float>& dst, const float* dev, size_t n) {
+    dst.resize(n);
+    UC_REQUIRE(dev != nullptr, "model: null weight pointer");
+    UC_CUDA_OK(cudaMemcpy(dst.data(), dev, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+static int upload(DevBuf& b, const std::vector<float>& src) {
+    if (int e = b.ensure(src.size() * sizeof(float))) return e;
+    UC_CUDA_OK(cudaMemcpy(b.p, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int pad_width(int w) {
+    for (int o : {32, 64, 128, 256})
+        if (w <= o) return o;
+    return 0;
+}
+
+// Per-level constants exactly as the reference kernel derives them (gridencoder.cu:L66-84,L137-139).
+static int build_grid(ucnerf_model* m, int li, const ucnerf_mlp_desc& md) {
+    LevelState& ls = m->lv[li];
+    const int L = md.grid_levels;
+    UC_REQUIRE(L >= 1 && L <= UCNERF_MAX_GRID_LEVELS, "model: grid_levels must be in [1,16]");
+    UC_REQUIRE(md.level_dim == 4, "model: the fused path requires level_dim == 4");
+    UC_REQUIRE(md.embeddings && md.offsets_host && md.grid_sizes_host, "model: null grid pointer");
+    m->offsets[li].assign(md.offsets_host, md.offsets_host + L + 1);
+    m->grid_sizes[li].assign(md.grid_sizes_host, md.grid_sizes_host + L);
+    ls.grid.table = reinterpret_cast<const float4*>(md.embeddings);
+    ls.grid.num_levels = L;
+    for (int l = 0; l < L; ++l) {
+        GridLevel& g = ls.grid.lv[l];
+        g.offset = (uint32_t)m->offsets[li][l];
+        g.hashmap_size = (uint32_t)(m->offsets[li][l + 1] - m->offsets[li][l]);
+        const float scale = exp2f((float)l * md.log2_per_level_scale) * (float)md.base_resolution - 1.0f;
+        const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+        g.scale = scale;
+        g.stride1 = resolution + 1;
+        uint32_t stride = 1;
+        for (int d = 0; d < 3 && stride <= g.hashmap_size; ++d) stride *= (resolution + 1);
+        g.hashed = stride > g.hashmap_size ? 1u : 0u;
+        g.pow2_mask = (g.hashmap_size & (g.hashmap_size - 1)) == 0 ? g.hashmap_size - 1 : 0u;
+        if (g.hashmap_size == 1) g.pow2_mask = 0;
+        const int64_t gs = m->grid_sizes[li][l];
+        g.grid_size = (float)gs;
+        ls.g2[l] = (float)(int32_t)(gs * gs);  // torch: int32 grid_sizes ** 2, promoted to fp32 in the product
+        g.pad = 0.f;
+    }
+    ls.lmax = sample_encode_lmax(L);
+    UC_REQUIRE(ls.lmax > 0, "model: unsupported number of grid levels");
+    return 0;
+}
+
+static int build_density_layer(ucnerf_model* m, int li, const ucnerf_mlp_desc& md, int out_dim) {
+    LevelState& ls = m->lv[li];
+    const int L = md.grid_levels, LC = L * 4, LP = ls.lmax * 4;
+    std::vector<float> w0, b0, w2, b2;
+    if (int e = fetch_host(w0, md.density0_w, (size_t)64 * LC)) return e;
+    if (int e = fetch_host(b0, md.density0_b, 64)) return e;
+    if (int e = fetch_host(w2, md.density2_w, (size_t)out_dim * 64)) return e;
+    if (int e = fetch_host(b2, md.density2_b, out_dim)) return e;
+    std::vector<float> w1p((size_t)64 * LP, 0.f);
+    for (int j = 0; j < 64; ++j)
+        for (int k = 0; k < LC; ++k) w1p[(size_t)j * LP + k] = w0[(size_t)j * LC + k];
+    if (int e = upload(ls.w1p, w1p)) return e;
+    if (int e = upload(ls.b1, b0)) return e;
+    std::vector<float> row0(w2.begin(), w2.begin() + 64);
+    if (int e = upload(ls.w2, row0)) return e;
+    ls.b2 = b2[0];
+    return 0;
+}
+
+static int build_color(ucnerf_model* m) {
+    const ucnerf_model_desc& d = m->d;
+    const int BW = d.bottleneck_width, W = d.net_width_viewdirs, ND = 3 + 6 * d.deg_view;
+    UC_REQUIRE(d.deg_view >= 0 && ND <= 32, "model: deg_view must be <= 4");
+    UC_REQUIRE(BW >= 1 && W >= 1, "model: bad MLP widths");
+    const int NP = pad_width(std::max(BW, W));
+    UC_REQUIRE(NP > 0, "model: bottleneck_width / net_width_viewdirs must be <= 256");
+    m->np = NP;
+    const int DIN = BW + ND;
+    std::vector<float> w2, b2, v0, c0, v1, c1, r, r0;
+    if (int e = fetch_host(w2, d.nerf.density2_w, (size_t)BW * 64)) return e;
+    if (int e = fetch_host(b2, d.nerf.density2_b, BW)) return e;
+    if (int e = fetch_host(v0, d.view0_w, (size_t)W * DIN)) return e;
+    if (int e = fetch_host(c0, d.view0_b, W)) return e;
+    if (int e = fetch_host(v1, d.view1_w, (size_t)W * (W + DIN))) return e;
+    if (int e = fetch_host(c1, d.view1_b, W)) return e;
+    if (int e = fetch_host(r, d.rgb_w, (size_t)3 * W)) return e;
+    if (int e = fetch_host(r0, d.rgb_b, 3)) return e;
+    // K-major ("transposed") zero-padded layouts: Wt[k][n]
+    std::vector<float> w2t((size_t)64 * NP, 0.f), b2p(NP, 0.f);
+    for (int n = 0; n < BW; ++n) {
+        b2p[n] = b2[n];
+        for (int k = 0; k < 64; ++k) w2t[(size_t)k * NP + n] = w2[(size_t)n * 64 + k];
+    }
+    std::vector<float> v0t((size_t)(NP + 32) * NP, 0.f), c0p(NP, 0.f);
+    for (int n = 0; n < W; ++n) {
+        c0p[n] = c0[n];
+        for (int k = 0; k < BW; ++k) v0t[(size_t)k * NP + n] = v0[(size_t)n * DIN + k];
+        for (int k = 0; k < ND; ++k) v0t[(size_t)(NP + k) * NP + n] = v0[(size_t)n * DIN + BW + k];
+    }
+    std::vector<float> v1t((size_t)(2 * NP + 32) * NP, 0.f), c1p(NP, 0.f);
+    for (int n = 0; n < W; ++n) {
+        c1p[n] = c1[n];
+        const float* src = &v1[(size_t)n * (W + DIN)];
+        for (int k = 0; k < W; ++k) v1t[(size_t)k * NP + n] = src[k];
+        for (int k = 0; k < BW; ++k) v1t[(size_t)(NP + k) * NP + n] = src[W + k];
+        for (int k = 0; k < ND; ++k) v1t[(size_t)(2 * NP + k) * NP + n] = src[W + BW + k];
+    }
+    std::vector<float> rt((size_t)NP * 4, 0.f), r0p(4, 0.f);
+    for (int c = 0; c < 3; ++c) {
+        r0p[c] = r0[c];
+        for (int k = 0; k < W; ++k) rt[(size_t)k * 4 + c] = r[(size_t)c * W + k];
+    }
+    if (int e = upload(m->w2t, w2t)) return e;
+    if (int e = upload(m->b2, b2p)) return e;
+    if (int e = upload(m->v0t, v0t)) return e;
+    if (int e = upload(m->c0, c0p)) return e;
+    if (int e = upload(m->v1t, v1t)) return e;
+    if (int e = upload(m->c1, c1p)) return e;
+    if (int e = upload(m->rt, rt)) return e;
+    if (int e = upload(m->r0, r0p)) return e;
+    return 0;
+}
+
+static int build_model(ucnerf_model* m, const ucnerf_model_desc* desc) {
+    m->d = *desc;
+    const ucnerf_model_desc& d = m->d;
+    UC_REQUIRE(d.num_prop_levels >= 1 && d.num_prop_levels <= UCNERF_MAX_PROP_LEVELS, "model: num_prop_levels must be in [1,4]");
+    UC_REQUIRE(d.num_prop_samples >= 2 && d.num_nerf_samples >= 2, "model: num_samples must be > 1");  // stepfun.py:L268
+    m->num_levels = d.num_prop_levels + 1;
+    make_cone_table(m->cone);
+    for (int li = 0; li < m->num_levels; ++li) {
+        const bool nerf = li == m->num_levels - 1;
+        const ucnerf_mlp_desc& md = nerf ? d.nerf : d.prop[li];
+        LevelState& ls = m->lv[li];
+        ls.S = nerf ? d.num_nerf_samples : d.num_prop_samples;
+        if (int e = build_grid(m, li, md)) return e;
+        if (int e = build_density_layer(m, li, md, nerf ? d.bottleneck_width : 1)) return e;
+        std::vector<float> u(ls.S);
+        deterministic_u(ls.S, u.data());
+        if (int e = upload(ls.u, u)) return e;
+    }
+    if (int e = build_color(m)) return e;
+    return 0;
+}
+
+static int time_begin(ucnerf_model* m, cudaStream_t st) {
+    if (m->timing) UC_CUDA_OK(cudaEventRecord(m->ev[0], st));
+    return 0;
+}
+static int time_end(ucnerf_model* m, cudaStream_t st, int slot) {
+    if (m->timing) {
+        UC_CUDA_OK(cudaEventRecord(m->ev[1], st));
+        UC_CUDA_OK(cudaEventSynchronize(m->ev[1]));
+        float t = 0.f;
+        UC_CUDA_OK(cudaEventElapsedTime(&t, m->ev[0], m->ev[1]));
+        m->ms[slot] += t;
+    }
+    return 0;
+}
+
+static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_t ray0, double train_frac,
+                        const ucnerf_outputs& o, cudaStream_t st) {
+    const ucnerf_model_desc& d = m->d;
+    RayPtrs rp{r.origins + 3 * ray0, r.directions + 3 * ray0, r.viewdirs + 3 * ray0, r.cam_dirs + 3 * ray0,
+               r.radii + ray0, r.near + ray0, r.far + ray0, r.rand_vec + 3 * ray0};
+    // models.py:L179-184 Schlick bias anneal
+    float anneal = 1.f;
+    if (d.anneal_slope > 0.0) {
+        const double s = d.anneal_slope, x = train_frac;
+        anneal = (float)((s * x) / ((s - 1.0) * x + 1.0));
+    }
+    int smax = 0;
+    for (int li = 0; li < m->num_levels; ++li) smax = std::max(smax, m->lv[li].S);
+    if (int e = m->density.ensure((size_t)n * smax * sizeof(float))) return e;
+
+    const float* t_prev = nullptr;
+    const float* w_prev = nullptr;
+    int n_prev = 1;
+    double prod = 1.0;
+    for (int li = 0; li < m->num_levels; ++li) {
+        LevelState& ls = m->lv[li];
+        const bool nerf = li == m->num_levels - 1;
+        const int S = ls.S;
+        float* sdist = o.sdist[li] ? o.sdist[li] + ray0 * (S + 1) : nullptr;
+        float* weights = o.weights[li] ? o.weights[li] + ray0 * S : nullptr;
+        if (!sdist) {
+            if (int e = ls.sdist.ensure((size_t)n * (S + 1) * sizeof(float))) return e;
+            sdist = ls.sdist.as<float>();
+        }
+        if (!weights) {
+            if (int e = ls.weights.ensure((size_t)n * S * sizeof(float))) return e;
+            weights = ls.weights.as<float>();
+        }
+        // models.py:L158-162
+        const float dilation = (float)(d.dilation_bias + d.dilation_multiplier * (1.0 - 0.0) / prod);
+        prod *= S;
+        const bool use_dil = (d.dilation_bias > 0.0 || d.dilation_multiplier > 0.0) && li > 0;
+
+        ResampleParams rs{};
+        rs.n_rays = n; rs.n_prev = n_prev; rs.t_prev = t_prev; rs.w_prev = w_prev; rs.dilate = use_dil ? 1 : 0;
+        rs.dilation = dilation; rs.anneal = anneal; rs.padding = (float)d.resample_padding; rs.S = S;
+        rs.u = ls.u.as<float>(); rs.out_sdist = sdist;
+        if (int e = time_begin(m, st)) return e;
+        if (int e = launch_resample(rs, st)) return e;
+        if (int e = time_end(m, st, 0)) return e;
+
+        SampleParams sp{};
+        sp.n_rays = n; sp.S = S; sp.rays = rp; sp.sdist = sdist; sp.grid = ls.grid; sp.cone = m->cone;
+        sp.std_scale = (float)d.std_scale; sp.density_bias = (float)d.density_bias;
+        sp.w1p = ls.w1p.as<float>(); sp.b1 = ls.b1.as<float>(); sp.w2 = ls.w2.as<float>(); sp.b2 = ls.b2;
+        sp.density = (nerf && o.sample_density) ? o.sample_density + ray0 * S : m->density.as<float>();
+        std::memcpy(sp.g2, ls.g2, sizeof(sp.g2));
+        float* rgb_s = nullptr;
+        if (nerf) {
+            if (int e = m->h1.ensure((size_t)n * S * 64 * sizeof(float))) return e;
+            sp.h1 = m->h1.as<float>();
+            if (o.sample_rgb) rgb_s = o.sample_rgb + ray0 * S * 3;
+            else {
+                if (int e = m->rgb_s.ensure((size_t)n * S * 3 * sizeof(float))) return e;
+                rgb_s = m->rgb_s.as<float>();
+            }
+        }
+        if (int e = time_begin(m, st)) return e;
+        if (int e = launch_sample_encode(sp, nerf, st)) return e;
+        if (int e = time_end(m, st, nerf ? 2 : 1)) return e;
+
+        if (nerf) {
+            ColorParams cp{};
+            cp.n_rows = n * (uint32_t)S; cp.S = S; cp.deg_view = d.deg_view; cp.h1 = sp.h1; cp.viewdirs = rp.viewdirs;
+            cp.w2t = m->w2t.as<float>(); cp.b2 = m->b2.as<float>(); cp.v0t = m->v0t.as<float>(); cp.c0 = m->c0.as<float>();
+            cp.v1t = m->v1t.as<float>(); cp.c1 = m->c1.as<float>(); cp.rt = m->rt.as<float>(); cp.r0 = m->r0.as<float>();
+            cp.rgb_scale = (float)(1.0 + 2.0 * d.rgb_padding); cp.rgb_padding = (float)d.rgb_padding; cp.rgb = rgb_s;
+            if (int e = time_begin(m, st)) return e;
+            if (int e = launch_color_mlp_simt(cp, m->np, st)) return e;
+            if (int e = time_end(m, st, 3)) return e;
+        }
+
+        CompositeParams cq{};
+        cq.n_rays = n; cq.S = S; cq.sdist = sdist; cq.density = sp.density; cq.rgb = rgb_s; cq.rays = rp;
+        cq.bg = (float)d.bg_intensity; cq.extras = 1; cq.weights = weights;
+        if (nerf) {
+            cq.o_rgb = o.rgb ? o.rgb + 3 * ray0 : nullptr;
+            cq.o_depth = o.depth ? o.depth + ray0 : nullptr;
+            cq.o_depth_raw = o.depth_raw ? o.depth_raw + ray0 : nullptr;
+            cq.o_acc = o.acc ? o.acc + ray0 : nullptr;
+            cq.o_mean = o.distance_mean ? o.distance_mean + ray0 : nullptr;
+            cq.o_median = o.distance_median ? o.distance_median + ray0 : nullptr;
+            cq.o_p5 = o.distance_percentile_5 ? o.distance_percentile_5 + ray0 : nullptr;
+            cq.o_p95 = o.distance_percentile_95 ? o.distance_percentile_95 + ray0 : nullptr;
+            cq.o_packed = o.packed ? o.packed + 12 * ray0 : nullptr;
+            cq.extras = (cq.o_mean || cq.o_median || cq.o_p5 || cq.o_p95 || cq.o_packed) ? 1 : 0;
+        } else {
+            cq.extras = 0;
+        }
+        if (int e = time_begin(m, st)) return e;
+        if (int e = launch_composite(cq, st)) return e;
+        if (int e = time_end(m, st, 4)) return e;
+
+        t_prev = sdist; w_prev = weights; n_prev = S;
+    }
+    return 0;
+}
+
+}  // namespace ucnerf
+
+extern "C" int ucnerf_abi_version(void) { return UCNERF_ABI_VERSION; }
+extern "C" const char* ucnerf_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t ucnerf_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" int ucnerf_model_create(const ucnerf_model_desc* desc, ucnerf_model** out) {
+    UC_REQUIRE(desc && out, "model_create: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("ucnerf_b200 requires a CUDA device (sm_100a); none is visible - there is no CPU fallback");
+        return 4;
+    }
+    ucnerf_model* m = new ucnerf_model();
+    if (int e = build_model(m, desc)) {
+        ucnerf_model_destroy(m);
+        return e;
+    }
+    if (cudaEventCreate(&m->ev[0]) != cudaSuccess || cudaEventCreate(&m->ev[1]) != cudaSuccess) {
+        set_error("model_create: cudaEventCreate failed");
+        ucnerf_model_destroy(m);
+        return 2;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" int ucnerf_model_refresh(ucnerf_model* m, const ucnerf_model_desc* desc, void* stream) {
+    UC_REQUIRE(m && desc, "model_refresh: null argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    UC_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return build_model(m, desc);
+}
+
+extern "C" int ucnerf_model_destroy(ucnerf_model* m) {
+    if (!m) return 0;
+    for (auto& ls : m->lv) { ls.w1p.release(); ls.b1.release(); ls.w2.release(); ls.u.release(); ls.sdist.release(); ls.weights.release(); }
+    for (DevBuf* b : {&m->w2t, &m->b2, &m->v0t, &m->c0, &m->v1t, &m->c1, &m->rt, &m->r0, &m->density, &m->h1, &m->rgb_s,
+                      &m->stage_in, &m->stage_out})
+        b->release();
+    if (m->ev[0]) cudaEventDestroy(m->ev[0]);
+    if (m->ev[1]) cudaEventDestroy(m->ev[1]);
+    delete m;
+    return 0;
+}
+
+extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value) {
+    UC_REQUIRE(m && key, "set_option: null argument");
+    const std::string k(key);
+    if (k == "chunk_rays") { UC_REQUIRE(value >= 1, "chunk_rays must be >= 1"); m->chunk_rays = value; }
+    else if (k == "color_mlp") { UC_REQUIRE(value == 0, "color_mlp: only mode 0 (fp32 SIMT) is built"); m->color_mode = (int)value; }
+    else if (k == "timing") m->timing = value != 0;
+    else { set_error("set_option: unknown key " + k); return 1; }
+    return 0;
+}
+
+extern "C" int ucnerf_get_timing(ucnerf_model* m, float* ms_out5, int reset) {
+    UC_REQUIRE(m && ms_out5, "get_timing: null argument");
+    for (int i = 0; i < 5; ++i) ms_out5[i] = m->ms[i];
+    if (reset) for (float& v : m->ms) v = 0.f;
+    return 0;
+}
+
+extern "C" int ucnerf_render_rays(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays* rays, double train_frac,
+                                  const ucnerf_outputs* out, void* stream) {
+    UC_REQUIRE(m && rays && out, "render_rays: null argument");
+    if (n_rays == 0) return 0;
+    UC_REQUIRE(rays->origins && rays->directions && rays->viewdirs && rays->cam_dirs && rays->radii && rays->near &&
+                   rays->far && rays->rand_vec,
+               "render_rays: every ray array (incl. rand_vec) must be provided");
+    std::lock_guard<std::mutex> lk(m->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (uint64_t r0 = 0; r0 < n_rays; r0 += (uint64_t)m->chunk_rays) {
+        const uint32_t n = (uint32_t)std::min<uint64_t>((uint64_t)m->chunk_rays, n_rays - r0);
+        if (int e = render_chunk(m, n, *rays, (size_t)r0, train_frac, *out, st)) return e;
+    }
+    return 0;
+}
+
+extern "C" int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays* rh, double train_frac,
+                                       const ucnerf_outputs* oh, void* stream) {
+    UC_REQUIRE(m && rh && oh, "render_rays_host: null argument");
+    if (n_rays == 0) return 0;
+    UC_REQUIRE(rh->origins && rh->directions && rh->viewdirs && rh->cam_dirs && rh->radii && rh->near && rh->far &&
+                   rh->rand_vec,
+               "render_rays_host: every ray array (incl. rand_vec) must be provided");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)n_rays;
+    // ---- stage inputs: 5 x [N,3] + 3 x [N] floats ----
+    if (int e = m->stage_in.ensure(N * 18 * sizeof(float))) return e;
+    float* base = m->stage_in.as<float>();
+    ucnerf_rays rd{};
+    const float* srcs[8] = {rh->origins, rh->directions, rh->viewdirs, rh->cam_dirs, rh->rand_vec, rh->radii, rh->near, rh->far};
+    const size_t widths[8] = {3, 3, 3, 3, 3, 1, 1, 1};
+    float* dsts[8];
+    size_t off = 0;
+    for (int i = 0; i < 8; ++i) {
+        dsts[i] = base + off;
+        UC_CUDA_OK(cudaMemcpyAsync(dsts[i], srcs[i], N * widths[i] * sizeof(float), cudaMemcpyHostToDevice, st));
+        off += N * widths[i];
+    }
+    rd.origins = dsts[0]; rd.directions = dsts[1]; rd.viewdirs = dsts[2]; rd.cam_dirs = dsts[3]; rd.rand_vec = dsts[4];
+    rd.radii = dsts[5]; rd.near = dsts[6]; rd.far = dsts[7];
+    // ---- stage outputs ----
+    const int nl = m->num_levels;
+    struct Slot { float* host; size_t floats; float** dev_field; };
+    ucnerf_outputs od{};
+    std::vector<Slot> slots;
+    auto add = [&](float* host, size_t per_ray, float** field) { if (host) slots.push_back({host, N * per_ray, field}); };
+    add(oh->rgb, 3, &od.rgb); add(oh->depth, 1, &od.depth); add(oh->depth_raw, 1, &od.depth_raw); add(oh->acc, 1, &od.acc);
+    add(oh->distance_mean, 1, &od.distance_mean); add(oh->distance_median, 1, &od.distance_median);
+    add(oh->distance_percentile_5, 1, &od.distance_percentile_5); add(oh->distance_percentile_95, 1, &od.distance_percentile_95);
+    for (int l = 0; l < nl; ++l) {
+        add(oh->sdist[l], (size_t)m->lv[l].S + 1, &od.sdist[l]);
+        add(oh->weights[l], (size_t)m->lv[l].S, &od.weights[l]);
+    }
+    add(oh->sample_rgb, (size_t)m->lv[nl - 1].S * 3, &od.sample_rgb);
+    add(oh->sample_density, (size_t)m->lv[nl - 1].S, &od.sample_density);
+    add(oh->packed, 12, &od.packed);
+    size_t tot = 0;
+    for (auto& s : slots) tot += (s.floats + 3) & ~size_t(3);
+    if (int e = m->stage_out.ensure(std::max<size_t>(tot, 4) * sizeof(float))) return e;
+    size_t o2 = 0;
+    for (auto& s : slots) { *s.dev_field = m->stage_out.as<float>() + o2; o2 += (s.floats + 3) & ~size_t(3); }
+    if (int e = ucnerf_render_rays(m, n_rays, &rd, train_frac, &od, stream)) return e;
+    for (auto& s : slots)
+        UC_CUDA_OK(cudaMemcpyAsync(s.host, *s.dev_field, s.floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    UC_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- small host-only helpers exported for the CPU test-suite (no GPU needed) ---------------------
+extern "C" int ucnerf_debug_u_grid(int S, float* out_host) {
+    UC_REQUIRE(S >= 1 && out_host, "debug_u_grid: bad argument");
+    deterministic_u(S, out_host);
+    return 0;
+}
+extern "C" int ucnerf_debug_cone_table(float* out30) {
+    UC_REQUIRE(out30, "debug_cone_table: null");
+    ConeTable ct;
+    make_cone_table(ct);
+    std::memcpy(out30, &ct, sizeof(float) * 30);
+    return 0;
+}

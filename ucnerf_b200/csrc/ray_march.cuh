@@ -1,0 +1,75 @@
+// Kernel parameter blocks + launch wrappers of the fused forward-render path (ray_march.cu).
+#pragma once
+#include "common.cuh"
+#include "ray_algos.cuh"
+
+namespace ucnerf {
+
+struct RayPtrs {
+    const float *origins, *directions, *viewdirs, *cam_dirs, *radii, *near, *far, *rand_vec;
+};
+
+struct ResampleParams {
+    uint32_t n_rays;
+    int n_prev;              // bins of the previous level (1 for the first level)
+    const float* t_prev;     // [N, n_prev+1] or NULL
+    const float* w_prev;     // [N, n_prev]   or NULL
+    int dilate;
+    float dilation, anneal, padding;
+    int S;
+    const float* u;          // [S]
+    float* out_sdist;        // [N, S+1]
+};
+
+struct SampleParams {
+    uint32_t n_rays;
+    int S;
+    RayPtrs rays;
+    const float* sdist;      // [N, S+1]
+    GridDesc grid;
+    ConeTable cone;
+    float std_scale, density_bias;
+    const float* w1p;        // [64][LMAX*4] zero padded
+    const float* b1;         // [64]
+    const float* w2;         // [64] (row 0 of density_layer.2)
+    float b2;
+    float* density;          // [N, S]
+    float* h1;               // [N*S, 64] (NeRF level only)
+    float g2[16];            // float(grid_sizes[l]^2)
+};
+
+struct ColorParams {
+    uint32_t n_rows;         // N * S
+    int S;
+    int deg_view;
+    const float* h1;         // [rows, 64]
+    const float* viewdirs;   // [N, 3]
+    const float *w2t, *b2;   // [64][NP], [NP]
+    const float *v0t, *c0;   // [NP+32][NP], [NP]
+    const float *v1t, *c1;   // [2NP+32][NP], [NP]
+    const float *rt, *r0;    // [NP][4], [4]
+    float rgb_scale, rgb_padding;   // (float)(1 + 2 pad), (float)pad
+    float* rgb;              // [rows, 3]
+};
+
+struct CompositeParams {
+    uint32_t n_rays;
+    int S;
+    const float* sdist;      // [N, S+1]
+    const float* density;    // [N, S]
+    const float* rgb;        // [N, S, 3] or NULL
+    RayPtrs rays;
+    float bg;
+    int extras;
+    float* weights;          // [N, S]
+    // optional per-ray outputs (NULL = skip)
+    float *o_rgb, *o_depth, *o_depth_raw, *o_acc, *o_mean, *o_median, *o_p5, *o_p95, *o_packed;
+};
+
+int launch_resample(const ResampleParams& p, cudaStream_t st);
+int launch_sample_encode(const SampleParams& p, bool nerf, cudaStream_t st);
+int launch_color_mlp_simt(const ColorParams& p, int np, cudaStream_t st);
+int launch_composite(const CompositeParams& p, cudaStream_t st);
+int sample_encode_lmax(int L);  // padded level count used by the kernel instantiation (0 = unsupported)
+
+}  // namespace ucnerf

@@ -1,0 +1,372 @@
+"""Host-side mirror of the reference's render surface for the eval hot path.
+
+  * `HotPathModel`    - owns a ucnerf_model handle built from a reference state_dict (same key names,
+                        SURVEY.md section 5 "checkpoint") and exposes
+                          .forward(rand, batch, train_frac, compute_extras, ...) -> (renderings, ray_history)
+                        with the contract of `Model.forward` (internal/models.py:L97-365, eval path), and
+                          .render_rays / .render_rays_host  (flat tensors in, dict of tensors out).
+  * `render_image`    - drop-in for `models.render_image` (internal/models.py:L907-1007): same signature, same
+                        keys in the returned dict.  Instead of slicing every 15k-ray chunk by rank and calling
+                        `accelerator.gather` on every leaf, each rank renders ONE contiguous tile of the image and
+                        the ranks exchange ONE packed [rays, 12] buffer with a single NCCL all-gather.
+
+PyTorch is used for device memory, streams and torch.distributed only; all arithmetic of the path runs in
+libucnerf_b200.so.  There is no fallback: without the library or without a CUDA device these raise."""
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PACKED_WIDTH = 12
+PACKED_FIELDS = ("rgb", "depth", "acc", "distance_mean", "distance_median", "distance_percentile_5",
+                 "distance_percentile_95", "depth_raw")
+_RAY_KEYS = ("origins", "directions", "viewdirs", "cam_dirs", "radii", "near", "far")
+
+
+def _grid_num_levels(desired, base=16, interval=2):
+    # internal/models.py:L425-426
+    return int(np.log(desired / base) / np.log(interval)) + 1
+
+
+class HotPathModel:
+    """B200 renderer for one UC-NeRF `Model` (proposal MLPs + NeRF MLP, waymo.gin-style)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], *, num_prop_samples: int, num_nerf_samples: int,
+                 num_prop_levels: Optional[int] = None, bottleneck_width: int = 256, net_width_viewdirs: int = 256,
+                 deg_view: int = 4, base_resolution: int = 16, dilation_multiplier: float = 0.5,
+                 dilation_bias: float = 0.0025, anneal_slope: float = 10.0, resample_padding: float = 0.0,
+                 std_scale: float = 0.5, bg_intensity: float = 1.0, density_bias: float = -1.0,
+                 rgb_padding: float = 0.001, vis_num_rays: int = 16, per_level_scales: Optional[Dict[str, float]] = None,
+                 device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.UcnerfError("ucnerf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if num_prop_levels is None:
+            num_prop_levels = len({k.split('.')[0] for k in state_dict if k.startswith('prop_mlp_')})
+        self.num_prop_levels = num_prop_levels
+        self.num_levels = num_prop_levels + 1
+        self.num_prop_samples, self.num_nerf_samples = num_prop_samples, num_nerf_samples
+        self.samples = [num_prop_samples] * num_prop_levels + [num_nerf_samples]
+        self.vis_num_rays = vis_num_rays
+        self._pls = dict(per_level_scales or {})
+        self._hyper = dict(bottleneck_width=bottleneck_width, net_width_viewdirs=net_width_viewdirs, deg_view=deg_view,
+                           base_resolution=base_resolution, dilation_multiplier=dilation_multiplier,
+                           dilation_bias=dilation_bias, anneal_slope=anneal_slope, resample_padding=resample_padding,
+                           std_scale=std_scale, bg_intensity=bg_intensity, density_bias=density_bias,
+                           rgb_padding=rgb_padding)
+        self._keep = {}      # device tensors the handle points into (embeddings) or was built from
+        self._handle = C.c_void_p()
+        self._build(state_dict, create=True)
+
+    # ---- construction -------------------------------------------------------------------------
+    @classmethod
+    def from_reference_model(cls, model, config=None, device=None):
+        """Build from a live reference `internal.models.Model` (reads its attributes + state_dict)."""
+        m = model.module if hasattr(model, "module") else model
+        nerf = m.nerf_mlp
+        if getattr(m, "raydist_fn", None) is not None:
+            raise NotImplementedError("fused path implements raydist_fn=None (waymo.gin) only")
+        if getattr(m, "num_glo_features", 0) > 0:
+            raise NotImplementedError("fused path does not implement GLO features")
+        if not (nerf.disable_density_normals and not nerf.disable_rgb):
+            raise NotImplementedError("fused path needs NerfMLP.disable_density_normals=True, disable_rgb=False")
+        bg = m.bg_intensity_range
+        if bg[0] != bg[1]:
+            raise NotImplementedError("fused path needs a constant background (bg_intensity_range min == max)")
+        sd = {k: v for k, v in m.state_dict().items()}
+        pls = {'nerf_mlp': float(nerf.encoder.per_level_scale)}
+        for i in range(m.num_levels - 1):
+            pls[f'prop_mlp_{i}'] = float(m.get_submodule(f'prop_mlp_{i}').encoder.per_level_scale)
+        return cls(sd, num_prop_samples=m.num_prop_samples, num_nerf_samples=m.num_nerf_samples,
+                   num_prop_levels=m.num_levels - 1, bottleneck_width=nerf.bottleneck_width,
+                   net_width_viewdirs=nerf.net_width_viewdirs, deg_view=nerf.deg_view,
+                   base_resolution=nerf.grid_base_resolution, dilation_multiplier=m.dilation_multiplier,
+                   dilation_bias=m.dilation_bias, anneal_slope=m.anneal_slope, resample_padding=m.resample_padding,
+                   std_scale=m.std_scale, bg_intensity=float(bg[0]), density_bias=nerf.density_bias,
+                   rgb_padding=nerf.rgb_padding,
+                   vis_num_rays=getattr(config, "vis_num_rays", 16) if config is not None else 16,
+                   per_level_scales=pls, device=device)
+
+    def _dev(self, t):
+        return t.detach().to(self.device, torch.float32).contiguous()
+
+    def _mlp_desc(self, sd, prefix, desc):
+        emb = self._dev(sd[prefix + '.encoder.embeddings'])
+        offsets = sd[prefix + '.encoder.offsets'].detach().cpu().to(torch.int32).contiguous()
+        grid_sizes = sd[prefix + '.encoder.grid_sizes'].detach().cpu().to(torch.int32).contiguous()
+        L = offsets.numel() - 1
+        C_ = emb.shape[1]
+        h = self._hyper
+        # per_level_scale as GridEncoder derives it (gridencoder/grid.py:L103-104) from the finest python-side
+        # resolution: grid_sizes[-1] - 1 == ceil(H * s^(L-1)); for the power-of-two grids of models.py this is exact.
+        desired = int(grid_sizes[-1].item()) - 1
+        pls = np.exp2(np.log2(desired / h['base_resolution']) / (L - 1)) if L > 1 else 2.0
+        pls = self._pls.get(prefix, pls)  # exact value when built from a live GridEncoder
+        w0, b0 = self._dev(sd[prefix + '.density_layer.0.weight']), self._dev(sd[prefix + '.density_layer.0.bias'])
+        w2, b2 = self._dev(sd[prefix + '.density_layer.2.weight']), self._dev(sd[prefix + '.density_layer.2.bias'])
+        self._keep[prefix] = (emb, offsets, grid_sizes, w0, b0, w2, b2)
+        desc.embeddings = emb.data_ptr()
+        desc.offsets_host = offsets.data_ptr()
+        desc.grid_sizes_host = grid_sizes.data_ptr()
+        desc.grid_levels, desc.level_dim = L, C_
+        desc.base_resolution = h['base_resolution']
+        desc.log2_per_level_scale = float(np.log2(pls))
+        desc.density0_w, desc.density0_b = w0.data_ptr(), b0.data_ptr()
+        desc.density2_w, desc.density2_b = w2.data_ptr(), b2.data_ptr()
+        if w0.shape != (64, L * C_):
+            raise ValueError(f"{prefix}.density_layer.0.weight has shape {tuple(w0.shape)}, expected (64, {L * C_})")
+
+    def _build(self, sd, create):
+        h = self._hyper
+        d = _lib.ModelDesc()
+        d.num_prop_levels = self.num_prop_levels
+        d.num_prop_samples, d.num_nerf_samples = self.num_prop_samples, self.num_nerf_samples
+        d.bottleneck_width, d.net_width_viewdirs, d.deg_view = h['bottleneck_width'], h['net_width_viewdirs'], h['deg_view']
+        for k in ("dilation_multiplier", "dilation_bias", "anneal_slope", "resample_padding", "std_scale",
+                  "bg_intensity", "density_bias", "rgb_padding"):
+            setattr(d, k, float(h[k]))
+        for i in range(self.num_prop_levels):
+            self._mlp_desc(sd, f'prop_mlp_{i}', d.prop[i])
+        self._mlp_desc(sd, 'nerf_mlp', d.nerf)
+        names = ('lin_second_stage_0.weight', 'lin_second_stage_0.bias', 'lin_second_stage_1.weight',
+                 'lin_second_stage_1.bias', 'rgb_layer.weight', 'rgb_layer.bias')
+        ts = [self._dev(sd['nerf_mlp.' + n]) for n in names]
+        self._keep['view'] = ts
+        (d.view0_w, d.view0_b, d.view1_w, d.view1_b, d.rgb_w, d.rgb_b) = [t.data_ptr() for t in ts]
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if create:
+                _lib.check(self.lib.ucnerf_model_create(C.byref(d), C.byref(self._handle)), "model_create")
+            else:
+                _lib.check(self.lib.ucnerf_model_refresh(self._handle, C.byref(d),
+                                                         torch.cuda.current_stream().cuda_stream), "model_refresh")
+
+    def refresh(self, state_dict):
+        """Re-read the weights (e.g. after an optimiser step)."""
+        self._build(state_dict, create=False)
+
+    def set_option(self, key: str, value: int):
+        _lib.check(self.lib.ucnerf_set_option(self._handle, key.encode(), int(value)), "set_option")
+
+    def timing(self, reset=True):
+        buf = (C.c_float * 5)()
+        _lib.check(self.lib.ucnerf_get_timing(self._handle, buf, int(reset)), "get_timing")
+        return dict(zip(("resample", "encode_prop", "encode_nerf", "color_mlp", "composite"), list(buf)))
+
+    def close(self):
+        if self._handle:
+            self.lib.ucnerf_model_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- rendering ----------------------------------------------------------------------------
+    def _out_spec(self, n, want):
+        S = self.samples
+        spec = {"rgb": (n, 3), "depth": (n,), "depth_raw": (n,), "acc": (n,), "distance_mean": (n,),
+                "distance_median": (n,), "distance_percentile_5": (n,), "distance_percentile_95": (n,),
+                "sample_rgb": (n, S[-1], 3), "sample_density": (n, S[-1]), "packed": (n, PACKED_WIDTH)}
+        for l in range(self.num_levels):
+            spec[f"sdist_{l}"] = (n, S[l] + 1)
+            spec[f"weights_{l}"] = (n, S[l])
+        unknown = set(want) - set(spec)
+        if unknown:
+            raise KeyError(f"unknown outputs {sorted(unknown)}")
+        return {k: spec[k] for k in want}
+
+    @staticmethod
+    def _fill_struct(o, bufs):
+        for k, t in bufs.items():
+            if k.startswith("sdist_"):
+                o.sdist[int(k[6:])] = t.data_ptr()
+            elif k.startswith("weights_"):
+                o.weights[int(k[8:])] = t.data_ptr()
+            else:
+                setattr(o, k, t.data_ptr())
+
+    def render_rays(self, batch: Dict[str, torch.Tensor], train_frac: float = 1.0, rand_vec=None,
+                    want=("rgb", "depth", "acc")) -> Dict[str, torch.Tensor]:
+        """batch: flat CUDA tensors origins/directions/viewdirs/cam_dirs [N,3], radii/near/far [N,1] or [N]."""
+        n = batch['origins'].shape[0]
+        rays = _lib.Rays()
+        keep = []
+        for k in _RAY_KEYS:
+            t = batch[k]
+            if t.device != self.device:
+                raise ValueError(f"batch['{k}'] is on {t.device}, renderer on {self.device}")
+            t = t.detach().to(torch.float32).contiguous()
+            keep.append(t)
+            setattr(rays, k, t.data_ptr())
+        if rand_vec is None:
+            rand_vec = batch.get('rand_vec')
+        if rand_vec is None:  # render.py:L140 draws it at every call
+            rand_vec = torch.randn_like(keep[3])
+        rand_vec = rand_vec.detach().to(self.device, torch.float32).contiguous()
+        rays.rand_vec = rand_vec.data_ptr()
+        spec = self._out_spec(n, want)
+        bufs = {k: torch.empty(shape, device=self.device, dtype=torch.float32) for k, shape in spec.items()}
+        o = _lib.Outputs()
+        self._fill_struct(o, bufs)
+        with torch.cuda.device(self.device):
+            rc = self.lib.ucnerf_render_rays(self._handle, n, C.byref(rays), float(train_frac), C.byref(o),
+                                             torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "render_rays")
+        return bufs
+
+    def render_rays_host(self, batch: Dict[str, torch.Tensor], train_frac: float = 1.0,
+                         want=("rgb", "depth", "acc"), out: Optional[Dict[str, torch.Tensor]] = None):
+        """Same with HOST tensors (pinned recommended): H2D, render, D2H inside the library call."""
+        n = batch['origins'].shape[0]
+        rays = _lib.Rays()
+        keep = []
+        for k in _RAY_KEYS + ("rand_vec",):
+            t = batch[k]
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"batch['{k}'] must be a contiguous float32 CPU tensor")
+            keep.append(t)
+            setattr(rays, k, t.data_ptr())
+        spec = self._out_spec(n, want)
+        if out is None:
+            out = {k: torch.empty(shape, dtype=torch.float32, pin_memory=True) for k, shape in spec.items()}
+        o = _lib.Outputs()
+        self._fill_struct(o, out)
+        with torch.cuda.device(self.device):
+            rc = self.lib.ucnerf_render_rays_host(self._handle, n, C.byref(rays), float(train_frac), C.byref(o),
+                                                  torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "render_rays_host")
+        return out
+
+    def forward(self, rand, batch, train_frac, compute_extras, zero_glo=True, eval_camidx=None, rand_vec=None):
+        """`Model.forward` contract for the eval path (internal/models.py:L97-365, heads excluded):
+        returns (renderings, ray_history), one entry per sampling level."""
+        if rand:
+            raise NotImplementedError("the fused path implements the deterministic eval path (rand=False)")
+        lead = batch['origins'].shape[:-1]
+        flat = {k: batch[k].reshape(-1, batch[k].shape[-1]) for k in _RAY_KEYS}
+        if rand_vec is None and batch.get('rand_vec') is not None:
+            rand_vec = batch['rand_vec'].reshape(-1, 3)
+        want = ["rgb", "depth", "acc", "sample_rgb", "sample_density"]
+        if compute_extras:
+            want += ["distance_mean", "distance_median", "distance_percentile_5", "distance_percentile_95"]
+        for l in range(self.num_levels):
+            want += [f"sdist_{l}", f"weights_{l}"]
+        out = self.render_rays(flat, train_frac, rand_vec, want)
+        renderings, history = [], []
+        nv = self.vis_num_rays
+        for l in range(self.num_levels):
+            last = l == self.num_levels - 1
+            r = {"weights": out[f"weights_{l}"].reshape(lead + (-1,))}
+            if last:
+                for k in ("rgb", "depth", "acc", "distance_mean", "distance_median", "distance_percentile_5",
+                          "distance_percentile_95"):
+                    if k in out:
+                        r[k] = out[k].reshape(lead + out[k].shape[1:])
+            if compute_extras:
+                r['ray_sdist'] = out[f"sdist_{l}"][:nv]
+                r['ray_weights'] = out[f"weights_{l}"][:nv]
+                if last:
+                    r['ray_rgbs'] = out["sample_rgb"][:nv]
+            renderings.append(r)
+            h = {"sdist": out[f"sdist_{l}"].reshape(lead + (-1,)), "weights": r["weights"]}
+            if last:
+                h["rgb"] = out["sample_rgb"].reshape(lead + out["sample_rgb"].shape[1:])
+                h["density"] = out["sample_density"].reshape(lead + (-1,))
+            history.append(h)
+        if compute_extras:  # models.py:L313-324: proposal levels show the final average colour
+            final_rgb = torch.sum(renderings[-1]['ray_rgbs'] * renderings[-1]['ray_weights'][..., None], dim=-2)
+            for l in range(self.num_levels - 1):
+                S = self.samples[l]
+                renderings[l]['ray_rgbs'] = final_rgb[:, None, :].expand(-1, S, -1)
+        return renderings, history
+
+
+def shard_bounds(num_rays: int, world: int, rank: int):
+    """Contiguous tile [start, stop) of rank `rank`; every rank renders ceil(num_rays / world) rays (the last
+    tiles are padded by re-rendering the final ray) so one fixed-size all-gather moves the image."""
+    per = (num_rays + world - 1) // world
+    start = min(rank * per, num_rays)
+    stop = min(start + per, num_rays)
+    return per, start, stop
+
+
+def _get_renderer(model, config):
+    m = model.module if hasattr(model, "module") else model
+    r = getattr(m, "_ucnerf_b200_renderer", None)
+    if r is None:
+        r = HotPathModel.from_reference_model(m, config)
+        object.__setattr__(m, "_ucnerf_b200_renderer", r)
+    return r
+
+
+@torch.no_grad()
+def render_image(model, accelerator, batch, rand, train_frac, config, verbose=True, return_weights=False,
+                 eval_camidx=0, rand_vec=None, renderer: Optional[HotPathModel] = None):
+    """Drop-in for internal/models.py:L907-1007 `render_image` (fused forward path, heads excluded).
+
+    model: a reference `Model` (a HotPathModel is built from it once and cached on the module) or None when
+    `renderer` is given.  accelerator: only process_index / num_processes are read."""
+    if rand:
+        raise NotImplementedError("render_image on the fused path is the deterministic eval path (rand=False)")
+    r = renderer if renderer is not None else _get_renderer(model, config)
+    height, width = batch['origins'].shape[:2]
+    num_rays = height * width
+    flat = {k: batch[k].reshape(num_rays, -1).to(r.device, non_blocking=True) for k in _RAY_KEYS}
+    if rand_vec is None:
+        rv = batch.get('rand_vec')
+        rand_vec = rv.reshape(num_rays, 3).to(r.device) if rv is not None else None
+    world = getattr(accelerator, "num_processes", 1) if accelerator is not None else 1
+    rank = getattr(accelerator, "process_index", 0) if accelerator is not None else 0
+    per, start, stop = shard_bounds(num_rays, world, rank)
+    idx = torch.arange(start, start + per, device=r.device).clamp_(max=num_rays - 1)
+    local = {k: v[idx] if (world > 1) else v for k, v in flat.items()}
+    if rand_vec is None:
+        # one draw for the whole image, identical on every rank would need a shared seed; the reference draws
+        # per rank (render.py:L140 under set_seed(device_specific=True)), so a per-rank draw matches it.
+        lrv = torch.randn_like(local['cam_dirs'])
+    else:
+        lrv = rand_vec[idx] if world > 1 else rand_vec
+    nl = r.num_levels
+    want = ["packed"] + [f"sdist_{l}" for l in range(nl)] + [f"weights_{l}" for l in range(nl)] + ["sample_rgb"]
+    out = r.render_rays(local, train_frac, lrv, want)
+    packed = out["packed"]
+    if world > 1:
+        import torch.distributed as dist
+        full = torch.empty((world * per, PACKED_WIDTH), device=r.device, dtype=torch.float32)
+        dist.all_gather_into_tensor(full, packed)  # the ONE collective per image
+        packed = full[:num_rays]
+    rendering = {
+        "rgb": packed[:, 0:3].reshape(height, width, 3),
+        "depth": packed[:, 3].reshape(height, width),
+        "acc": packed[:, 4].reshape(height, width),
+        "distance_mean": packed[:, 5].reshape(height, width),
+        "distance_median": packed[:, 6].reshape(height, width),
+        "distance_percentile_5": packed[:, 7].reshape(height, width),
+        "distance_percentile_95": packed[:, 8].reshape(height, width),
+    }
+    wl = out[f"weights_{nl - 1}"]
+    if world > 1 and return_weights:
+        import torch.distributed as dist
+        fw = torch.empty((world * per, wl.shape[1]), device=r.device, dtype=torch.float32)
+        dist.all_gather_into_tensor(fw, wl.contiguous())
+        wl = fw[:num_rays]
+    if world == 1 or return_weights:
+        rendering["weights"] = wl.reshape(height, width, -1)
+    # ray bundles for vis.visualize_suite: a random subset of vis_num_rays of this rank's rays per level
+    nv = r.vis_num_rays
+    n_local = stop - start
+    pick = torch.randperm(max(n_local, 1))[:nv].to(r.device)
+    final_rgb = torch.sum(out["sample_rgb"][pick] * out[f"weights_{nl - 1}"][pick][..., None], dim=-2)
+    rendering["ray_sdist"] = [out[f"sdist_{l}"][pick] for l in range(nl)]
+    rendering["ray_weights"] = [out[f"weights_{l}"][pick] for l in range(nl)]
+    rendering["ray_rgbs"] = [final_rgb[:, None, :].expand(-1, r.samples[l], -1) for l in range(nl - 1)] + \
+                            [out["sample_rgb"][pick]]
+    return rendering

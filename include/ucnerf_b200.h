@@ -163,10 +163,11 @@ uint64_t ucnerf_launch_count(void);
 /* Tunables: "chunk_rays" (rays per internal chunk), "color_mlp" (0 = fp32 SIMT, 1 = tensor core). */
 int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value);
 
-/* Timing probe: when enabled (value != 0) ucnerf_render_rays records CUDA events around each kernel
- * family and ucnerf_get_timing returns accumulated milliseconds: [resample, encode_prop, encode_nerf,
- * color_mlp, composite]. */
-int ucnerf_get_timing(ucnerf_model* m, float* ms_out5, int reset);
+/* Timing probe: with option "timing" != 0, ucnerf_render_rays records a CUDA event pair around every kernel
+ * launch on the launch stream (no synchronisation is added).  ucnerf_get_timing waits for the recorded events
+ * and returns accumulated device milliseconds and launch counts per kernel family:
+ * [resample, encode_prop, encode_nerf, color_mlp, composite].  launches_out5 may be NULL. */
+int ucnerf_get_timing(ucnerf_model* m, float* ms_out5, uint32_t* launches_out5, int reset);
 
 #ifdef __cplusplus
 }

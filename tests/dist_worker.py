@@ -1,0 +1,96 @@
+"""Worker for the world_size-2 tests of render_image's tile shard + single all-gather.
+--backend nccl : real renderer on 2 GPUs, compared with a single-GPU render of the whole image.
+--backend gloo : CPU stand-in renderer (a deterministic function of the rays) so the host-side shard / pad /
+                 gather / reshape logic is exercised without a GPU."""
+import argparse
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from ucnerf_b200 import render as R  # noqa: E402
+
+
+class FakeRenderer:
+    """Same surface as HotPathModel.render_rays, on CPU: outputs are simple functions of the ray origin."""
+    num_levels, samples, vis_num_rays = 2, [8, 4], 4
+    device = torch.device("cpu")
+
+    def render_rays(self, batch, train_frac, rand_vec, want):
+        o = batch["origins"]
+        n = o.shape[0]
+        out = {}
+        packed = torch.zeros(n, R.PACKED_WIDTH)
+        packed[:, 0:3] = o
+        packed[:, 3] = o.sum(-1)
+        packed[:, 4] = o[:, 0] * 2
+        for i in range(5, 10):
+            packed[:, i] = o[:, 1] + i
+        out["packed"] = packed
+        for l, S in enumerate(self.samples):
+            out[f"sdist_{l}"] = torch.linspace(0, 1, S + 1).expand(n, S + 1).contiguous()
+            out[f"weights_{l}"] = o[:, :1].expand(n, S).contiguous()
+        out["sample_rgb"] = o[:, None, :].expand(n, self.samples[-1], 3).contiguous()
+        return {k: out[k] for k in want}
+
+
+class Acc:
+    def __init__(self):
+        self.process_index = dist.get_rank()
+        self.num_processes = dist.get_world_size()
+        self.is_main_process = self.process_index == 0
+
+
+class Cfg:
+    render_chunk_size, vis_num_rays = 15000, 4
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--backend", default="gloo")
+    a = ap.parse_args()
+    dist.init_process_group(a.backend)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    H, W = 37, 53  # 1961 rays: not divisible by the world size -> padding path
+    g = torch.Generator().manual_seed(0)
+    if a.backend == "gloo":
+        origins = torch.rand((H, W, 3), generator=g)
+        batch = {k: origins for k in ("origins", "directions", "viewdirs", "cam_dirs")}
+        batch.update({k: origins[..., :1] for k in ("radii", "near", "far")})
+        img = R.render_image(None, Acc(), batch, False, 1.0, Cfg(), renderer=FakeRenderer(), return_weights=True,
+                             rand_vec=torch.zeros(H * W, 3))
+        assert torch.equal(img["rgb"], origins)
+        assert torch.equal(img["depth"], origins.sum(-1)) and torch.equal(img["acc"], origins[..., 0] * 2)
+        assert torch.equal(img["distance_percentile_95"], origins[..., 1] + 8)
+        assert img["weights"].shape == (H, W, 4) and torch.equal(img["weights"][..., 0], origins[..., 0])
+        assert len(img["ray_sdist"]) == 2 and img["ray_rgbs"][0].shape == (4, 8, 3)
+    else:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle import cases, ucnerf_oracle as O
+        from test_gpu_render import build_renderer
+        cfg, params, _ = cases.make_case("waymo", 1)
+        r = build_renderer(cfg, params)
+        rays = O.synthetic_rays(H * W, seed=77)
+        b2d = {k: v.reshape(H, W, -1).cuda() for k, v in rays.items()}
+        rv = b2d["rand_vec"].reshape(-1, 3)
+        img = R.render_image(None, Acc(), b2d, False, 1.0, Cfg(), renderer=r, rand_vec=rv)
+
+        class One:
+            process_index, num_processes, is_main_process = 0, 1, True
+
+        ref = R.render_image(None, One(), b2d, False, 1.0, Cfg(), renderer=r, rand_vec=rv)
+        for k in ("rgb", "depth", "acc", "distance_mean", "distance_median"):
+            assert torch.equal(img[k], ref[k]), k
+    dist.barrier()
+    if rank == 0:
+        print("DIST_OK", a.backend, world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

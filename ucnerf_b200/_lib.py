@@ -116,7 +116,7 @@ def load():
     lib.ucnerf_render_rays.argtypes = [vp, C.c_uint64, C.POINTER(Rays), C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_render_rays_host.argtypes = [vp, C.c_uint64, C.POINTER(Rays), C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
-    lib.ucnerf_get_timing.argtypes = [vp, c_float_p, C.c_int]
+    lib.ucnerf_get_timing.argtypes = [vp, c_float_p, C.POINTER(C.c_uint32), C.c_int]
     lib.ucnerf_debug_u_grid.argtypes = [C.c_int, vp]
     lib.ucnerf_debug_cone_table.argtypes = [vp]
     for name in EXPORTS:

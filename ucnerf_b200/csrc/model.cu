@@ -77,7 +77,11 @@ struct ucnerf_model {
     int color_mode = 0;
     bool timing = false;
     float ms[5] = {0, 0, 0, 0, 0};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    uint32_t nlaunch[5] = {0, 0, 0, 0, 0};
+    struct Timed { cudaEvent_t a, b; int slot; };
+    std::vector<Timed> pending;            // recorded, not yet resolved (no sync on the launch path)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+    cudaEvent_t cur_a = nullptr, cur_b = nullptr;
     std::mutex mu;
 };
 
@@ -230,18 +234,38 @@ static int build_model(ucnerf_model* m, const ucnerf_model_desc* desc) {
     return 0;
 }
 
+// Per-kernel-family timing: an event pair is recorded around each launch on the launch stream and resolved
+// later in ucnerf_get_timing, so enabling it adds no synchronisation to the timed region.
 static int time_begin(ucnerf_model* m, cudaStream_t st) {
-    if (m->timing) UC_CUDA_OK(cudaEventRecord(m->ev[0], st));
+    if (!m->timing) return 0;
+    if (m->pool.empty()) {
+        cudaEvent_t a, b;
+        UC_CUDA_OK(cudaEventCreate(&a));
+        UC_CUDA_OK(cudaEventCreate(&b));
+        m->pool.emplace_back(a, b);
+    }
+    m->cur_a = m->pool.back().first;
+    m->cur_b = m->pool.back().second;
+    m->pool.pop_back();
+    UC_CUDA_OK(cudaEventRecord(m->cur_a, st));
     return 0;
 }
 static int time_end(ucnerf_model* m, cudaStream_t st, int slot) {
-    if (m->timing) {
-        UC_CUDA_OK(cudaEventRecord(m->ev[1], st));
-        UC_CUDA_OK(cudaEventSynchronize(m->ev[1]));
-        float t = 0.f;
-        UC_CUDA_OK(cudaEventElapsedTime(&t, m->ev[0], m->ev[1]));
-        m->ms[slot] += t;
+    if (!m->timing) return 0;
+    UC_CUDA_OK(cudaEventRecord(m->cur_b, st));
+    m->pending.push_back({m->cur_a, m->cur_b, slot});
+    return 0;
+}
+static int resolve_timing(ucnerf_model* m) {
+    for (auto& t : m->pending) {
+        UC_CUDA_OK(cudaEventSynchronize(t.b));
+        float ms = 0.f;
+        UC_CUDA_OK(cudaEventElapsedTime(&ms, t.a, t.b));
+        m->ms[t.slot] += ms;
+        m->nlaunch[t.slot] += 1;
+        m->pool.emplace_back(t.a, t.b);
     }
+    m->pending.clear();
     return 0;
 }
 
@@ -366,11 +390,6 @@ extern "C" int ucnerf_model_create(const ucnerf_model_desc* desc, ucnerf_model**
         ucnerf_model_destroy(m);
         return e;
     }
-    if (cudaEventCreate(&m->ev[0]) != cudaSuccess || cudaEventCreate(&m->ev[1]) != cudaSuccess) {
-        set_error("model_create: cudaEventCreate failed");
-        ucnerf_model_destroy(m);
-        return 2;
-    }
     *out = m;
     return 0;
 }
@@ -388,8 +407,8 @@ extern "C" int ucnerf_model_destroy(ucnerf_model* m) {
     for (DevBuf* b : {&m->w2t, &m->b2, &m->v0t, &m->c0, &m->v1t, &m->c1, &m->rt, &m->r0, &m->density, &m->h1, &m->rgb_s,
                       &m->stage_in, &m->stage_out})
         b->release();
-    if (m->ev[0]) cudaEventDestroy(m->ev[0]);
-    if (m->ev[1]) cudaEventDestroy(m->ev[1]);
+    resolve_timing(m);
+    for (auto& e : m->pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete m;
     return 0;
 }
@@ -404,10 +423,15 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
     return 0;
 }
 
-extern "C" int ucnerf_get_timing(ucnerf_model* m, float* ms_out5, int reset) {
+extern "C" int ucnerf_get_timing(ucnerf_model* m, float* ms_out5, uint32_t* launches_out5, int reset) {
     UC_REQUIRE(m && ms_out5, "get_timing: null argument");
-    for (int i = 0; i < 5; ++i) ms_out5[i] = m->ms[i];
-    if (reset) for (float& v : m->ms) v = 0.f;
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (int e = resolve_timing(m)) return e;
+    for (int i = 0; i < 5; ++i) {
+        ms_out5[i] = m->ms[i];
+        if (launches_out5) launches_out5[i] = m->nlaunch[i];
+    }
+    if (reset) for (int i = 0; i < 5; ++i) { m->ms[i] = 0.f; m->nlaunch[i] = 0; }
     return 0;
 }
 

@@ -154,9 +154,12 @@ class HotPathModel:
         _lib.check(self.lib.ucnerf_set_option(self._handle, key.encode(), int(value)), "set_option")
 
     def timing(self, reset=True):
-        buf = (C.c_float * 5)()
-        _lib.check(self.lib.ucnerf_get_timing(self._handle, buf, int(reset)), "get_timing")
-        return dict(zip(("resample", "encode_prop", "encode_nerf", "color_mlp", "composite"), list(buf)))
+        """Per kernel family: (device milliseconds, launches) accumulated since the last reset; needs
+        set_option("timing", 1)."""
+        buf, cnt = (C.c_float * 5)(), (C.c_uint32 * 5)()
+        _lib.check(self.lib.ucnerf_get_timing(self._handle, buf, cnt, int(reset)), "get_timing")
+        names = ("resample", "encode_prop", "encode_nerf", "color_mlp", "composite")
+        return {n: (float(buf[i]), int(cnt[i])) for i, n in enumerate(names)}
 
     def close(self):
         if self._handle:

@@ -63,7 +63,7 @@ struct GridLevel {
     uint32_t pow2_mask;     // hashmap_size-1 if power of two else 0 (then use %)
     float scale;            // exp2f(l*S)*H - 1
     float grid_size;        // python-side grid_sizes[l] (erf down-weighting), as float
-    float pad;
+    uint32_t mod_mode;      // 0: index needs no reduction, 1: & pow2_mask, 2: % hashmap_size
 };
 
 struct GridDesc {

@@ -132,7 +132,9 @@ static int build_grid(ucnerf_model* m, int li, const ucnerf_mlp_desc& md) {
         const int64_t gs = m->grid_sizes[li][l];
         g.grid_size = (float)gs;
         ls.g2[l] = (float)(int32_t)(gs * gs);  // torch: int32 grid_sizes ** 2, promoted to fp32 in the product
-        g.pad = 0.f;
+        // dense index of an in-range point: max = (res+1)^3 - 1 < hashmap_size  => no modulo needed
+        if (!g.hashed) g.mod_mode = 0;
+        else g.mod_mode = g.pow2_mask ? 1u : 2u;
     }
     ls.lmax = sample_encode_lmax(L);
     UC_REQUIRE(ls.lmax > 0, "model: unsupported number of grid levels");
@@ -176,34 +178,42 @@ static int build_color(ucnerf_model* m) {
     if (int e = fetch_host(c1, d.view1_b, W)) return e;
     if (int e = fetch_host(r, d.rgb_w, (size_t)3 * W)) return e;
     if (int e = fetch_host(r0, d.rgb_b, 3)) return e;
-    // K-major ("transposed") zero-padded layouts: Wt[k][n]
-    std::vector<float> w2t((size_t)64 * NP, 0.f), b2p(NP, 0.f);
-    for (int n = 0; n < BW; ++n) {
-        b2p[n] = b2[n];
-        for (int k = 0; k < 64; ++k) w2t[(size_t)k * NP + n] = w2[(size_t)n * 64 + k];
-    }
-    std::vector<float> v0t((size_t)(NP + 32) * NP, 0.f), c0p(NP, 0.f);
+    // Fold the activation-free bottleneck layer x = W2 h1 + b2 into its consumers (fp64 on the host):
+    //   V0 [x, dir] + c0 = (V0x W2) h1 + V0d dir + (c0 + V0x b2)        (likewise for V1's x block)
+    // K-major ("transposed") zero-padded layouts Wt[k][n]; K rows: [h1 (64) | direnc (32)].
+    std::vector<float> p0t((size_t)96 * NP, 0.f), c0p(NP, 0.f);
     for (int n = 0; n < W; ++n) {
-        c0p[n] = c0[n];
-        for (int k = 0; k < BW; ++k) v0t[(size_t)k * NP + n] = v0[(size_t)n * DIN + k];
-        for (int k = 0; k < ND; ++k) v0t[(size_t)(NP + k) * NP + n] = v0[(size_t)n * DIN + BW + k];
+        const float* vr = &v0[(size_t)n * DIN];
+        double bacc = c0[n];
+        for (int j = 0; j < BW; ++j) bacc += (double)vr[j] * (double)b2[j];
+        c0p[n] = (float)bacc;
+        for (int k = 0; k < 64; ++k) {
+            double acc = 0.0;
+            for (int j = 0; j < BW; ++j) acc += (double)vr[j] * (double)w2[(size_t)j * 64 + k];
+            p0t[(size_t)k * NP + n] = (float)acc;
+        }
+        for (int k = 0; k < ND; ++k) p0t[(size_t)(64 + k) * NP + n] = vr[BW + k];
     }
-    std::vector<float> v1t((size_t)(2 * NP + 32) * NP, 0.f), c1p(NP, 0.f);
+    std::vector<float> v1t((size_t)(NP + 96) * NP, 0.f), c1p(NP, 0.f);
     for (int n = 0; n < W; ++n) {
-        c1p[n] = c1[n];
         const float* src = &v1[(size_t)n * (W + DIN)];
+        double bacc = c1[n];
+        for (int j = 0; j < BW; ++j) bacc += (double)src[W + j] * (double)b2[j];
+        c1p[n] = (float)bacc;
         for (int k = 0; k < W; ++k) v1t[(size_t)k * NP + n] = src[k];
-        for (int k = 0; k < BW; ++k) v1t[(size_t)(NP + k) * NP + n] = src[W + k];
-        for (int k = 0; k < ND; ++k) v1t[(size_t)(2 * NP + k) * NP + n] = src[W + BW + k];
+        for (int k = 0; k < 64; ++k) {
+            double acc = 0.0;
+            for (int j = 0; j < BW; ++j) acc += (double)src[W + j] * (double)w2[(size_t)j * 64 + k];
+            v1t[(size_t)(NP + k) * NP + n] = (float)acc;
+        }
+        for (int k = 0; k < ND; ++k) v1t[(size_t)(NP + 64 + k) * NP + n] = src[W + BW + k];
     }
     std::vector<float> rt((size_t)NP * 4, 0.f), r0p(4, 0.f);
     for (int c = 0; c < 3; ++c) {
         r0p[c] = r0[c];
         for (int k = 0; k < W; ++k) rt[(size_t)k * 4 + c] = r[(size_t)c * W + k];
     }
-    if (int e = upload(m->w2t, w2t)) return e;
-    if (int e = upload(m->b2, b2p)) return e;
-    if (int e = upload(m->v0t, v0t)) return e;
+    if (int e = upload(m->v0t, p0t)) return e;
     if (int e = upload(m->c0, c0p)) return e;
     if (int e = upload(m->v1t, v1t)) return e;
     if (int e = upload(m->c1, c1p)) return e;
@@ -338,7 +348,7 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         if (nerf) {
             ColorParams cp{};
             cp.n_rows = n * (uint32_t)S; cp.S = S; cp.deg_view = d.deg_view; cp.h1 = sp.h1; cp.viewdirs = rp.viewdirs;
-            cp.w2t = m->w2t.as<float>(); cp.b2 = m->b2.as<float>(); cp.v0t = m->v0t.as<float>(); cp.c0 = m->c0.as<float>();
+            cp.p0t = m->v0t.as<float>(); cp.c0 = m->c0.as<float>();
             cp.v1t = m->v1t.as<float>(); cp.c1 = m->c1.as<float>(); cp.rt = m->rt.as<float>(); cp.r0 = m->r0.as<float>();
             cp.rgb_scale = (float)(1.0 + 2.0 * d.rgb_padding); cp.rgb_padding = (float)d.rgb_padding; cp.rgb = rgb_s;
             if (int e = time_begin(m, st)) return e;

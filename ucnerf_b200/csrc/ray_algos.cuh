@@ -414,7 +414,12 @@ UC_HD uint32_t level_index(const GridLevel& lv, uint32_t x, uint32_t y, uint32_t
     uint32_t idx;
     if (lv.hashed) idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
     else idx = x + y * lv.stride1 + z * lv.stride1 * lv.stride1;
-    return lv.pow2_mask ? (idx & lv.pow2_mask) : (idx % lv.hashmap_size);
+    // `index % hashmap_size` (gridencoder.cu:L83): hashed levels have power-of-two tables (AND mask); a dense
+    // index of an in-range point is already < (res+1)^3 <= hashmap_size, so no reduction is needed there.
+    // mod_mode: 0 = none, 1 = mask, 2 = generic modulo (non power-of-two hashed table).
+    if (lv.mod_mode == 1) return idx & lv.pow2_mask;
+    if (lv.mod_mode == 2) return idx % lv.hashmap_size;
+    return idx;
 }
 
 struct CellCoords {

@@ -38,15 +38,18 @@ struct SampleParams {
     float g2[16];            // float(grid_sizes[l]^2)
 };
 
+// Colour MLP with the linear bottleneck layer folded into its two consumers (exact algebra, see model.cu):
+//   a   = relu(P0 [h1, direnc] + c0')          P0  = [V0x W2 | V0d]          c0' = c0 + V0x b2
+//   a2  = relu(V1a a + P1 [h1, direnc] + c1')  P1  = [V1x W2 | V1d]          c1' = c1 + V1x b2
+//   rgb = sigmoid(R a2 + r0) * (1 + 2 pad) - pad
 struct ColorParams {
     uint32_t n_rows;         // N * S
     int S;
     int deg_view;
     const float* h1;         // [rows, 64]
     const float* viewdirs;   // [N, 3]
-    const float *w2t, *b2;   // [64][NP], [NP]
-    const float *v0t, *c0;   // [NP+32][NP], [NP]
-    const float *v1t, *c1;   // [2NP+32][NP], [NP]
+    const float *p0t, *c0;   // [96][NP], [NP]          rows: h1 (64), direnc (32, zero padded)
+    const float *v1t, *c1;   // [NP + 96][NP], [NP]     rows: a (NP), h1 (64), direnc (32)
     const float *rt, *r0;    // [NP][4], [4]
     float rgb_scale, rgb_padding;   // (float)(1 + 2 pad), (float)pad
     float* rgb;              // [rows, 3]

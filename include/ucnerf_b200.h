@@ -160,7 +160,8 @@ int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays*
 /* Number of kernels launched by this library in this process so far (bench.py's gpu_launches). */
 uint64_t ucnerf_launch_count(void);
 
-/* Tunables: "chunk_rays" (rays per internal chunk), "color_mlp" (0 = fp32 SIMT, 1 = tensor core). */
+/* Tunables: "chunk_rays" (rays per internal chunk), "color_mlp" (0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = auto:
+ * tensor cores whenever the MLP widths allow, the default), "timing" (see ucnerf_get_timing). */
 int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value);
 
 /* Timing probe: with option "timing" != 0, ucnerf_render_rays records a CUDA event pair around every kernel

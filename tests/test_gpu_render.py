@@ -202,3 +202,26 @@ def test_two_gpu_tile_shard_and_single_allgather():
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "DIST_OK" in res.stdout
+
+
+def test_tensor_core_color_mlp_matches_simt_and_oracle():
+    """tcgen05 3xTF32 colour MLP (default for W=256) vs the fp32 SIMT kernel vs the reference per-sample colours."""
+    cfg, params, batch, r = case("waymo")
+    g = load_golden("waymo")
+    r.set_option("color_mlp", 1)
+    tc = run(r, batch)
+    r.set_option("color_mlp", 0)
+    simt = run(r, batch)
+    r.set_option("color_mlp", 2)
+    e_tc = np.abs(tc["sample_rgb"] - g["sample_rgb"]).max()
+    e_simt = np.abs(simt["sample_rgb"] - g["sample_rgb"]).max()
+    print("sample_rgb max err: tensor-core", e_tc, "simt", e_simt, "tc-vs-simt", np.abs(tc["sample_rgb"] - simt["sample_rgb"]).max())
+    assert e_tc < 2e-5 and e_simt < 2e-5
+    assert np.abs(tc["rgb"] - g["rgb"]).max() < TOL and np.abs(simt["rgb"] - g["rgb"]).max() < TOL
+    # ragged row count (not a multiple of the 128-row tile) and a tiny batch
+    for n in (1, 3, 130):
+        sub = {k: v[:n] for k, v in batch.items()}
+        r.set_option("color_mlp", 1)
+        a = run(r, sub)
+        r.set_option("color_mlp", 2)
+        np.testing.assert_allclose(a["rgb"], g["rgb"][:n], atol=TOL)

@@ -1,0 +1,434 @@
+// Colour MLP on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate through the 3xTF32 split.
+//
+//   a   = relu(P0 [h1, direnc] + c0')            (K = 96,  N = 256)      -> TMEM accumulator "acc3"
+//   a2  = relu(P1 [h1, direnc] + V1a a + c1')    (K = 352, N = 256)      -> TMEM accumulator "acc4"
+//   rgb = sigmoid(R a2 + r0) * (1 + 2 pad) - pad (N = 3, CUDA cores in the epilogue)
+// (the activation-free bottleneck layer of models.py:L438-441/L601 is folded into P0 / P1 on the host.)
+//
+// Why 3xTF32: the parity bar is rgb L-inf < 1e-4 against an fp32 reference.  One TF32 pass (10-bit mantissa)
+// leaves ~1e-3 on the pre-activations.  Splitting x = hi + lo (both TF32-representable) and accumulating
+// hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator keeps ~2^-21 relative error per product at 3 MMAs per
+// k-step, still ~5x the fp32 CUDA-core rate.
+//
+// CTA = one 128-row tile at a time (persistent over tiles), 6 warps:
+//   warps 0-3  producer / epilogue: thread t owns row t.  Builds the A operand chunk by chunk in shared memory
+//              in the UMMA canonical K-major SWIZZLE_128B layout (hi tile + lo tile): from global h1 / the
+//              computed view-direction encoding, or from acc3 in TMEM (tcgen05.ld -> +bias -> relu -> split).
+//              Finally drains acc4, applies the rgb layer + sigmoid and writes the sample colours.
+//   warp 4     one elected thread issues tcgen05.mma (M=128, N=256, K=8, kind::tf32) and tcgen05.commit.
+//   warp 5     one elected thread streams the pre-swizzled weight chunks (hi|lo, 64 KB each) from L2 with
+//              cp.async.bulk (TMA bulk copy, completes on an mbarrier).
+// Pipelines: A ring (2 x 32 KB) and B ring (2 x 64 KB) with full/empty mbarriers; acc3/acc4 full/empty
+// mbarriers order MMA vs. TMEM drains.  TMEM: all 512 columns (acc3 = [0,256), acc4 = [256,512)).
+#include <cstring>
+
+#include "ray_march.cuh"
+
+namespace ucnerf {
+
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kN = 256;
+constexpr int kKC = 32;                       // K elements per chunk = one 128-byte swizzle row
+constexpr int kSteps = 14;                    // chunks per tile (see kStep* below)
+constexpr uint32_t kATileBytes = kTileM * kKC * 4;   // 16 KB (one of hi / lo)
+constexpr uint32_t kASlotBytes = 2 * kATileBytes;    // 32 KB
+constexpr uint32_t kBTileBytes = kN * kKC * 4;       // 32 KB
+constexpr uint32_t kBSlotBytes = 2 * kBTileBytes;    // 64 KB
+constexpr int kStages = 2;
+constexpr uint32_t kSmemA = 0;
+constexpr uint32_t kSmemB = kSmemA + kStages * kASlotBytes;            // 65536
+constexpr uint32_t kSmemMisc = kSmemB + kStages * kBSlotBytes;         // 196608
+// misc region: barriers (16 x 8 B), tmem ptr, then c0[256], c1[256], R[256] float4, r0[4]
+constexpr uint32_t kOffBar = 0;
+constexpr uint32_t kOffTmem = 128;
+constexpr uint32_t kOffC0 = 256;
+constexpr uint32_t kOffC1 = kOffC0 + 1024;
+constexpr uint32_t kOffR = kOffC1 + 1024;
+constexpr uint32_t kOffR0 = kOffR + 4096;
+constexpr uint32_t kMiscBytes = kOffR0 + 16;
+constexpr uint32_t kSmemTotal = kSmemMisc + kMiscBytes + 1024;  // +1024: manual 1 KB alignment slack
+constexpr int kThreads = 192;
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
+// a/b K-major, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+enum Bar { A_FULL0 = 0, A_FULL1, A_EMPTY0, A_EMPTY1, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, ACC3_FULL, ACC4_FULL,
+           ACC3_EMPTY, ACC4_EMPTY, NUM_BARS };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug or a faulted copy must surface as an error code, never as a hung GPU.  The first
+// thread whose wait exceeds kWatchdogNs records where it was stuck in p.dbg and raises the abort flag; every other
+// wait loop polls the flag and bails out, so the kernel drains and the host reports the record.
+constexpr unsigned long long kWatchdogNs = 400ull * 1000 * 1000;
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t* dbg, uint32_t tag, uint32_t bar_id,
+                                            uint32_t it, uint32_t step) {
+    const unsigned long long t0 = gtimer();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 255u) == 0) {
+            if (*reinterpret_cast<volatile uint32_t*>(dbg) != 0u) return false;
+            if (gtimer() - t0 > kWatchdogNs) {
+                if (atomicCAS(dbg, 0u, tag) == 0u) {
+                    dbg[1] = blockIdx.x; dbg[2] = threadIdx.x; dbg[3] = bar_id; dbg[4] = parity; dbg[5] = it; dbg[6] = step;
+                    __threadfence();
+                }
+                return false;
+            }
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t* dbg, uint32_t tag, uint32_t bar_id,
+                                          uint32_t it, uint32_t step) {
+    if (mbar_try_wait(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity, dbg, tag, bar_id, it, step);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// write one row (32 fp32 values) of an A chunk as hi / lo TF32 tiles in the SWIZZLE_128B K-major layout
+__device__ __forceinline__ void store_a_row(uint8_t* slot, int row, const float (&v)[32]) {
+    uint8_t* base = slot + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint4 hi, lo;
+        uint32_t h;
+        h = to_tf32(v[4 * c + 0]); hi.x = h; lo.x = to_tf32(v[4 * c + 0] - __uint_as_float(h));
+        h = to_tf32(v[4 * c + 1]); hi.y = h; lo.y = to_tf32(v[4 * c + 1] - __uint_as_float(h));
+        h = to_tf32(v[4 * c + 2]); hi.z = h; lo.z = to_tf32(v[4 * c + 2] - __uint_as_float(h));
+        h = to_tf32(v[4 * c + 3]); hi.w = h; lo.w = to_tf32(v[4 * c + 3] - __uint_as_float(h));
+        const int pc = (c ^ (row & 7)) * 16;
+        *reinterpret_cast<uint4*>(base + pc) = hi;
+        *reinterpret_cast<uint4*>(base + kATileBytes + pc) = lo;
+    }
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+// Step table of one tile (A chunk source, weight chunk = step index in the blob, accumulator):
+//   0: h1[0:32]  x P0   -> acc3 (init)      3: h1[0:32]  x P1 -> acc4 (init)     6..13: a[32j:32j+32] x V1a -> acc4
+//   1: h1[32:64] x P0   -> acc3             4: h1[32:64] x P1 -> acc4
+//   2: direnc    x P0   -> acc3, commit     5: direnc    x P1 -> acc4                  13: commit acc4
+__global__ void __launch_bounds__(kThreads, 1)
+color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* misc = smem + kSmemMisc;
+    const uint32_t bar0 = smem_u32(misc + kOffBar);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(misc + kOffTmem);
+    float* sC0 = reinterpret_cast<float*>(misc + kOffC0);
+    float* sC1 = reinterpret_cast<float*>(misc + kOffC1);
+    float4* sR = reinterpret_cast<float4*>(misc + kOffR);
+    float* sR0 = reinterpret_cast<float*>(misc + kOffR0);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < 256; i += kThreads) {
+        sC0[i] = p.c0[i];
+        sC1[i] = p.c1[i];
+        sR[i] = reinterpret_cast<const float4*>(p.rt)[i];
+    }
+    if (threadIdx.x < 4) sR0[threadIdx.x] = p.r0[threadIdx.x];
+    if (threadIdx.x == 0) {
+        mbar_init(BAR(A_FULL0), 128); mbar_init(BAR(A_FULL1), 128);
+        mbar_init(BAR(A_EMPTY0), 1); mbar_init(BAR(A_EMPTY1), 1);
+        mbar_init(BAR(B_FULL0), 1); mbar_init(BAR(B_FULL1), 1);
+        mbar_init(BAR(B_EMPTY0), 1); mbar_init(BAR(B_EMPTY1), 1);
+        mbar_init(BAR(ACC3_FULL), 1); mbar_init(BAR(ACC4_FULL), 1);
+        mbar_init(BAR(ACC3_EMPTY), 128); mbar_init(BAR(ACC4_EMPTY), 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {  // whole warp: allocate all 512 TMEM columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(misc + kOffTmem)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const uint32_t ntiles = (p.n_rows + kTileM - 1) / kTileM;
+
+    if (warp < 4) {
+        // ================= producer / epilogue: thread t <-> row t of the tile =====================
+        const int t = threadIdx.x;
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        uint32_t slot = 0, phase = 0, it = 0;
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t row = tile * kTileM + t;
+            const bool valid = row < p.n_rows;
+            const float* h1row = p.h1 + (size_t)(valid ? row : 0) * 64;
+            float vd[3] = {0.f, 0.f, 0.f};
+            if (valid) {
+                const uint32_t ray = row / (uint32_t)p.S;
+                vd[0] = p.viewdirs[3 * (size_t)ray]; vd[1] = p.viewdirs[3 * (size_t)ray + 1]; vd[2] = p.viewdirs[3 * (size_t)ray + 2];
+            }
+#pragma unroll 1
+            for (int c = 0; c < kSteps; ++c) {
+                float v[32];
+                if (c == 0 || c == 1 || c == 3 || c == 4) {
+                    const float4* src = reinterpret_cast<const float4*>(h1row + ((c == 0 || c == 3) ? 0 : 32));
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 x = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                    }
+                } else if (c == 2 || c == 5) {  // coord.py:L214-225 pos_enc(viewdirs, 0, 4) -> 27 values, zero padded
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                    if (valid) {
+                        v[0] = vd[0]; v[1] = vd[1]; v[2] = vd[2];
+#pragma unroll
+                        for (int d = 0; d < 4; ++d)
+#pragma unroll
+                            for (int ax = 0; ax < 3; ++ax) {
+                                const float x = fm(vd[ax], (float)(1 << d));
+                                v[3 + 3 * d + ax] = sinf(x);
+                                v[15 + 3 * d + ax] = sinf(fa(x, 1.57079637f));
+                            }
+                    }
+                } else {
+                    const int j = c - 6;
+                    if (j == 0) {
+                        if (!mbar_wait(BAR(ACC3_FULL), it & 1, p.dbg, 1, ACC3_FULL, it, c)) goto teardown;
+                        tc_fence_after();
+                    }
+                    uint32_t r[32];
+                    tmem_ld32(lane_taddr + (uint32_t)(32 * j), r);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(__uint_as_float(r[i]) + sC0[32 * j + i], 0.f);
+                    if (j == 7) {  // acc3 fully drained: the MMA warp may overwrite it for the next tile
+                        tc_fence_before();
+                        mbar_arrive(BAR(ACC3_EMPTY));
+                    }
+                }
+                if (!mbar_wait(BAR(A_EMPTY0 + slot), phase ^ 1, p.dbg, 2, A_EMPTY0 + slot, it, c)) goto teardown;
+                store_a_row(smem + kSmemA + slot * kASlotBytes, t, v);
+                fence_proxy_async();
+                mbar_arrive(BAR(A_FULL0 + slot));
+                slot ^= 1;
+                phase ^= (slot == 0);
+            }
+            // ---- final epilogue: a2 = relu(acc4 + c1'), rgb layer, sigmoid ----
+            if (!mbar_wait(BAR(ACC4_FULL), it & 1, p.dbg, 3, ACC4_FULL, it, 99)) goto teardown;
+            tc_fence_after();
+            float o0 = sR0[0], o1 = sR0[1], o2 = sR0[2];
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                uint32_t r[32];
+                tmem_ld32(lane_taddr + (uint32_t)(256 + 32 * j), r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float a2 = fmaxf(__uint_as_float(r[i]) + sC1[32 * j + i], 0.f);
+                    const float4 w = sR[32 * j + i];
+                    o0 = fmaf(a2, w.x, o0);
+                    o1 = fmaf(a2, w.y, o1);
+                    o2 = fmaf(a2, w.z, o2);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(BAR(ACC4_EMPTY));
+            if (valid) {
+                float* o = p.rgb + (size_t)row * 3;
+                o[0] = fs(fm(sigmoid_f(o0), p.rgb_scale), p.rgb_padding);
+                o[1] = fs(fm(sigmoid_f(o1), p.rgb_scale), p.rgb_padding);
+                o[2] = fs(fm(sigmoid_f(o2), p.rgb_scale), p.rgb_padding);
+            }
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer (one thread) ==================================================
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0, it = 0;
+            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+#pragma unroll 1
+                for (int s = 0; s < kSteps; ++s) {
+                    if (s == 0 && !mbar_wait(BAR(ACC3_EMPTY), (it & 1) ^ 1, p.dbg, 4, ACC3_EMPTY, it, s)) goto teardown;
+                    if (s == 3 && !mbar_wait(BAR(ACC4_EMPTY), (it & 1) ^ 1, p.dbg, 5, ACC4_EMPTY, it, s)) goto teardown;
+                    if (!mbar_wait(BAR(B_FULL0 + slot), phase, p.dbg, 6, B_FULL0 + slot, it, s)) goto teardown;
+                    if (!mbar_wait(BAR(A_FULL0 + slot), phase, p.dbg, 7, A_FULL0 + slot, it, s)) goto teardown;
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + kSmemA + slot * kASlotBytes);
+                    const uint32_t a_lo = a_hi + kATileBytes;
+                    const uint32_t b_hi = smem_u32(smem + kSmemB + slot * kBSlotBytes);
+                    const uint32_t b_lo = b_hi + kBTileBytes;
+                    const uint32_t acc = tmem_base + (s < 3 ? 0u : 256u);
+                    const bool init = (s == 0 || s == 3);
+#pragma unroll
+                    for (int ks = 0; ks < kKC / 8; ++ks) {
+                        const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
+                        const uint64_t dbh = make_desc(b_hi + ks * 32), dbl = make_desc(b_lo + ks * 32);
+                        umma_tf32(acc, dah, dbh, (init && ks == 0) ? 0u : 1u);
+                        umma_tf32(acc, dal, dbh, 1u);
+                        umma_tf32(acc, dah, dbl, 1u);
+                    }
+                    umma_commit(BAR(A_EMPTY0 + slot));
+                    umma_commit(BAR(B_EMPTY0 + slot));
+                    if (s == 2) umma_commit(BAR(ACC3_FULL));
+                    if (s == kSteps - 1) umma_commit(BAR(ACC4_FULL));
+                    slot ^= 1;
+                    phase ^= (slot == 0);
+                }
+            }
+        }
+    } else {
+        // ================= weight loader (one thread): pre-swizzled hi|lo chunks, L2 -> smem ==========
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0, it = 0;
+            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+#pragma unroll 1
+                for (int s = 0; s < kSteps; ++s) {
+                    if (!mbar_wait(BAR(B_EMPTY0 + slot), phase ^ 1, p.dbg, 8, B_EMPTY0 + slot, it, s)) goto teardown;
+                    mbar_expect_tx(BAR(B_FULL0 + slot), kBSlotBytes);
+                    bulk_g2s(smem_u32(smem + kSmemB + slot * kBSlotBytes), p.wblob + (size_t)s * kBSlotBytes, kBSlotBytes,
+                             BAR(B_FULL0 + slot));
+                    slot ^= 1;
+                    phase ^= (slot == 0);
+                }
+            }
+        }
+    }
+
+teardown:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+static uint32_t* g_tc_dbg = nullptr;   // [16] words: watchdog record of color_mlp_tc_kernel (0 = healthy)
+
+int color_tc_status(uint32_t* out16) {
+    for (int i = 0; i < 16; ++i) out16[i] = 0;
+    if (!g_tc_dbg) return 0;
+    UC_CUDA_OK(cudaDeviceSynchronize());
+    UC_CUDA_OK(cudaMemcpy(out16, g_tc_dbg, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int launch_color_mlp_tc(const ColorTcParams& p_in, cudaStream_t st) {
+    if (p_in.n_rows == 0) return 0;
+    if (!g_tc_dbg) {
+        UC_CUDA_OK(cudaMalloc(&g_tc_dbg, 16 * sizeof(uint32_t)));
+        UC_CUDA_OK(cudaMemset(g_tc_dbg, 0, 16 * sizeof(uint32_t)));
+    }
+    ColorTcParams p = p_in;
+    p.dbg = g_tc_dbg;
+    static bool configured = false;
+    if (!configured) {
+        UC_CUDA_OK(cudaFuncSetAttribute(color_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal));
+        configured = true;
+    }
+    const uint32_t ntiles = (p.n_rows + kTileM - 1) / kTileM;
+    const uint32_t blocks = ntiles < (uint32_t)kNumSMs ? ntiles : (uint32_t)kNumSMs;
+    color_mlp_tc_kernel<<<blocks, kThreads, kSmemTotal, st>>>(p);
+    UC_LAUNCH_CHECK();
+    return 0;
+}
+
+uint32_t color_tc_blob_bytes() { return kSteps * kBSlotBytes; }
+
+// Host: lay the folded weights out as the kernel consumes them.  Wt chunks are K-major [k][256] fp32 arrays of 32
+// rows each (step order of the kernel); every chunk becomes hi tile | lo tile, each in the UMMA K-major
+// SWIZZLE_128B image: element (n, k) at (n/8)*1024 + (n%8)*128 + ((k/4) ^ (n%8))*16 + (k%4)*4.
+static inline uint32_t tf32_rna_bits(float x) {
+    uint32_t b;
+    memcpy(&b, &x, 4);
+    if ((b & 0x7F800000u) == 0x7F800000u) return b;
+    b += 0x1000u;
+    return b & 0xFFFFE000u;
+}
+void color_tc_pack_chunk(const float* wt_rows /* [32][256] */, uint8_t* dst /* 64 KB */) {
+    for (int n = 0; n < kN; ++n)
+        for (int k = 0; k < kKC; ++k) {
+            const float w = wt_rows[(size_t)k * kN + n];
+            const uint32_t hb = tf32_rna_bits(w);
+            float hf;
+            memcpy(&hf, &hb, 4);
+            const uint32_t lb = tf32_rna_bits(w - hf);
+            const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((k >> 2) ^ (n & 7)) * 16) + (k & 3) * 4;
+            memcpy(dst + off, &hb, 4);
+            memcpy(dst + kBTileBytes + off, &lb, 4);
+        }
+}
+
+}  // namespace ucnerf

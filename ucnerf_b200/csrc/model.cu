@@ -69,12 +69,13 @@ struct ucnerf_model {
     LevelState lv[UCNERF_MAX_PROP_LEVELS + 1];
     ConeTable cone;
     int np = 0;  // padded colour-MLP width
-    DevBuf w2t, b2, v0t, c0, v1t, c1, rt, r0;
+    DevBuf w2t, b2, v0t, c0, v1t, c1, rt, r0, wblob;
+    bool tc_ok = false;   // tensor-core colour MLP available for these shapes (W = 256, deg_view = 4)
     DevBuf density, h1, rgb_s;
     // host-entry staging
     DevBuf stage_in, stage_out;
     int64_t chunk_rays = 65536;
-    int color_mode = 0;
+    int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 3xTF32 (error if shapes unsupported), 2 = auto
     bool timing = false;
     float ms[5] = {0, 0, 0, 0, 0};
     uint32_t nlaunch[5] = {0, 0, 0, 0, 0};
@@ -214,6 +215,17 @@ static int build_color(ucnerf_model* m) {
         for (int k = 0; k < W; ++k) rt[(size_t)k * 4 + c] = r[(size_t)c * W + k];
     }
     if (int e = upload(m->v0t, p0t)) return e;
+    m->tc_ok = (NP == 256 && d.deg_view == 4);
+    if (m->tc_ok) {
+        // step order of color_mlp_tc_kernel: P0 rows [h1 0:32, h1 32:64, dir], P1 rows [h1 0:32, h1 32:64, dir], V1a x8
+        std::vector<uint8_t> blob(color_tc_blob_bytes());
+        const size_t cb = blob.size() / 14;
+        for (int s = 0; s < 3; ++s) color_tc_pack_chunk(&p0t[(size_t)(32 * s) * NP], blob.data() + cb * s);
+        for (int s = 0; s < 3; ++s) color_tc_pack_chunk(&v1t[(size_t)(NP + 32 * s) * NP], blob.data() + cb * (3 + s));
+        for (int j = 0; j < 8; ++j) color_tc_pack_chunk(&v1t[(size_t)(32 * j) * NP], blob.data() + cb * (6 + j));
+        if (int e = m->wblob.ensure(blob.size())) return e;
+        UC_CUDA_OK(cudaMemcpy(m->wblob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    }
     if (int e = upload(m->c0, c0p)) return e;
     if (int e = upload(m->v1t, v1t)) return e;
     if (int e = upload(m->c1, c1p)) return e;
@@ -352,7 +364,17 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
             cp.v1t = m->v1t.as<float>(); cp.c1 = m->c1.as<float>(); cp.rt = m->rt.as<float>(); cp.r0 = m->r0.as<float>();
             cp.rgb_scale = (float)(1.0 + 2.0 * d.rgb_padding); cp.rgb_padding = (float)d.rgb_padding; cp.rgb = rgb_s;
             if (int e = time_begin(m, st)) return e;
-            if (int e = launch_color_mlp_simt(cp, m->np, st)) return e;
+            const bool use_tc = m->color_mode == 1 || (m->color_mode == 2 && m->tc_ok);
+            if (use_tc) {
+                UC_REQUIRE(m->tc_ok, "color_mlp=1 (tensor core) needs net_width_viewdirs/bottleneck <= 256 padded to 256 and deg_view == 4");
+                ColorTcParams tp{};
+                tp.n_rows = cp.n_rows; tp.S = S; tp.h1 = cp.h1; tp.viewdirs = cp.viewdirs;
+                tp.wblob = m->wblob.as<uint8_t>(); tp.c0 = cp.c0; tp.c1 = cp.c1; tp.rt = cp.rt; tp.r0 = cp.r0;
+                tp.rgb_scale = cp.rgb_scale; tp.rgb_padding = cp.rgb_padding; tp.rgb = cp.rgb;
+                if (int e = launch_color_mlp_tc(tp, st)) return e;
+            } else {
+                if (int e = launch_color_mlp_simt(cp, m->np, st)) return e;
+            }
             if (int e = time_end(m, st, 3)) return e;
         }
 
@@ -415,7 +437,7 @@ extern "C" int ucnerf_model_destroy(ucnerf_model* m) {
     if (!m) return 0;
     for (auto& ls : m->lv) { ls.w1p.release(); ls.b1.release(); ls.w2.release(); ls.u.release(); ls.sdist.release(); ls.weights.release(); }
     for (DevBuf* b : {&m->w2t, &m->b2, &m->v0t, &m->c0, &m->v1t, &m->c1, &m->rt, &m->r0, &m->density, &m->h1, &m->rgb_s,
-                      &m->stage_in, &m->stage_out})
+                      &m->stage_in, &m->stage_out, &m->wblob})
         b->release();
     resolve_timing(m);
     for (auto& e : m->pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -427,7 +449,7 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
     UC_REQUIRE(m && key, "set_option: null argument");
     const std::string k(key);
     if (k == "chunk_rays") { UC_REQUIRE(value >= 1, "chunk_rays must be >= 1"); m->chunk_rays = value; }
-    else if (k == "color_mlp") { UC_REQUIRE(value == 0, "color_mlp: only mode 0 (fp32 SIMT) is built"); m->color_mode = (int)value; }
+    else if (k == "color_mlp") { UC_REQUIRE(value >= 0 && value <= 2, "color_mlp: 0 = fp32 SIMT, 1 = tensor core, 2 = auto"); m->color_mode = (int)value; }
     else if (k == "timing") m->timing = value != 0;
     else { set_error("set_option: unknown key " + k); return 1; }
     return 0;
@@ -510,7 +532,23 @@ extern "C" int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const u
     for (auto& s : slots)
         UC_CUDA_OK(cudaMemcpyAsync(s.host, *s.dev_field, s.floats * sizeof(float), cudaMemcpyDeviceToHost, st));
     UC_CUDA_OK(cudaStreamSynchronize(st));
+    {
+        uint32_t wd[16];
+        if (int e = color_tc_status(wd)) return e;
+        if (wd[0] != 0) {
+            set_error("color_mlp_tc: pipeline watchdog fired (tag " + std::to_string(wd[0]) + ", barrier " +
+                      std::to_string(wd[3]) + ", step " + std::to_string(wd[6]) + ")");
+            return 5;
+        }
+    }
     return 0;
+}
+
+// Watchdog record of the tensor-core colour MLP (synchronises the device): out16[0] != 0 means a pipeline wait
+// timed out; [1..6] = block, thread, barrier id, parity, tile iteration, step.
+extern "C" int ucnerf_debug_tc_status(uint32_t* out16) {
+    UC_REQUIRE(out16, "debug_tc_status: null");
+    return color_tc_status(out16);
 }
 
 // ---- small host-only helpers exported for the CPU test-suite (no GPU needed) ---------------------

@@ -55,6 +55,20 @@ struct ColorParams {
     float* rgb;              // [rows, 3]
 };
 
+// tensor-core variant (color_mlp_tc.cu): W = 256, deg_view = 4 only; weights pre-split / pre-swizzled (wblob)
+struct ColorTcParams {
+    uint32_t n_rows;
+    int S;
+    const float* h1;         // [rows, 64]
+    const float* viewdirs;   // [N, 3]
+    const uint8_t* wblob;    // 14 chunks x (hi tile | lo tile) in UMMA K-major SWIZZLE_128B layout
+    const float *c0, *c1;    // [256] folded biases
+    const float *rt, *r0;    // [256][4], [4]
+    float rgb_scale, rgb_padding;
+    float* rgb;              // [rows, 3]
+    uint32_t* dbg;           // watchdog record (set by the launcher)
+};
+
 struct CompositeParams {
     uint32_t n_rays;
     int S;
@@ -73,6 +87,10 @@ int launch_resample(const ResampleParams& p, cudaStream_t st);
 int launch_sample_encode(const SampleParams& p, bool nerf, cudaStream_t st);
 int launch_color_mlp_simt(const ColorParams& p, int np, cudaStream_t st);
 int launch_composite(const CompositeParams& p, cudaStream_t st);
+int launch_color_mlp_tc(const ColorTcParams& p, cudaStream_t st);
+uint32_t color_tc_blob_bytes();
+int color_tc_status(uint32_t* out16);
+void color_tc_pack_chunk(const float* wt_rows, uint8_t* dst);
 int sample_encode_lmax(int L);  // padded level count used by the kernel instantiation (0 = unsupported)
 
 }  // namespace ucnerf

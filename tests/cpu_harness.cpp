@@ -74,6 +74,7 @@ void h_grid_features(int B, int L, const uint32_t* lvdesc, const float* table, c
         for (int l = 0; l < L; ++l) {
             GridLevel lv;
             lv.offset = lvdesc[6 * l]; lv.hashmap_size = lvdesc[6 * l + 1]; lv.stride1 = lvdesc[6 * l + 2];
+            lv.stride2 = lv.stride1 * lv.stride1;
             lv.hashed = lvdesc[6 * l + 3]; lv.pow2_mask = lvdesc[6 * l + 4];
             lv.mod_mode = !lv.hashed ? 0u : (lv.pow2_mask ? 1u : 2u);
             std::memcpy(&lv.scale, &lvdesc[6 * l + 5], 4);

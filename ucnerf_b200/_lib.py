@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libucnerf_b200.so")
+LIB_PATH = os.environ.get("UCNERF_B200_LIB") or os.path.join(_HERE, "libucnerf_b200.so")  # env: A/B builds
 
 MAX_GRID_LEVELS = 16
 MAX_PROP_LEVELS = 4

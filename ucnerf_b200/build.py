@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libucnerf_b200.so")
 OBJ = os.path.join(HERE, "csrc", "build")
-SOURCES = ["grid_encode.cu", "ray_march.cu", "color_mlp_tc.cu", "model.cu"]
+SOURCES = ["grid_encode.cu", "ray_march.cu", "sample_encode.cu", "color_mlp_tc.cu", "model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -22,16 +22,18 @@ def _newer(target, deps):
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(verbose=True, force=False, extra_flags=()):
+def build(verbose=True, force=False, extra_flags=(), out=None, obj_dir=None):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    os.makedirs(OBJ, exist_ok=True)
+    OUT_ = out or OUT
+    OBJ_ = obj_dir or OBJ
+    os.makedirs(OBJ_, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "ucnerf_b200.h"))
     jobs = []
     objs = []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJ, s.replace(".cu", ".o"))
+        obj = os.path.join(OBJ_, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or not _newer(obj, [src] + headers):
             jobs.append([nvcc, *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj])
@@ -47,9 +49,9 @@ def build(verbose=True, force=False, extra_flags=()):
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         list(ex.map(run, jobs))
-    if jobs or force or not os.path.exists(OUT):
-        run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs])
-    return OUT
+    if jobs or force or not os.path.exists(OUT_):
+        run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT_, *objs])
+    return OUT_
 
 
 if __name__ == "__main__":

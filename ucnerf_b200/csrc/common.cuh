@@ -59,6 +59,7 @@ struct GridLevel {
     uint32_t offset;        // entry offset of the level inside `embeddings`
     uint32_t hashmap_size;  // entries in the level
     uint32_t stride1;       // resolution + 1 (align_corners=False): dense index stride
+    uint32_t stride2;       // stride1 * stride1
     uint32_t hashed;        // 1: XOR-prime hash, 0: dense index
     uint32_t pow2_mask;     // hashmap_size-1 if power of two else 0 (then use %)
     float scale;            // exp2f(l*S)*H - 1

@@ -125,6 +125,7 @@ static int build_grid(ucnerf_model* m, int li, const ucnerf_mlp_desc& md) {
         const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
         g.scale = scale;
         g.stride1 = resolution + 1;
+        g.stride2 = g.stride1 * g.stride1;
         uint32_t stride = 1;
         for (int d = 0; d < 3 && stride <= g.hashmap_size; ++d) stride *= (resolution + 1);
         g.hashed = stride > g.hashmap_size ? 1u : 0u;

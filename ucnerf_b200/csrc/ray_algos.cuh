@@ -366,8 +366,8 @@ struct ConeInterval {
 };
 UC_HD ConeInterval make_cone_interval(float t0, float t1) {
     ConeInterval ci;
-    const float tm = fd(fa(t0, t1), 2.f);
-    const float td = fd(fs(t1, t0), 2.f);
+    const float tm = fm(fa(t0, t1), 0.5f);  // x/2 == x*0.5 exactly
+    const float td = fm(fs(t1, t0), 0.5f);
     const float td2 = fm(td, td), tm2 = fm(tm, tm);
     const float A = fa(td2, fm(3.f, tm2));
     // torch evaluates t_m ** 4 with a <=1-ulp pow; rounding the exact fp64 product reproduces it
@@ -403,9 +403,9 @@ UC_HD void cone_point(const RayGeom& rg, const ConeInterval& ci, const ConeTable
         const float c = fd(powf(fs(fm(2.f, mag), 1.f), 0.33333334f), mag);
         sd = fm(fm(c, c), sd);
     }
-    sigma = fd(sd, 2.f);
+    sigma = fm(sd, 0.5f);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) g[i] = fd(fa(fd(x[i], 2.f), 1.f), 2.f);
+    for (int i = 0; i < 3; ++i) g[i] = fm(fa(fm(x[i], 0.5f), 1.f), 0.5f);
 }
 
 // ---- hash-grid lookup on the fused path (D=3, C=4, gridtype=hash, align_corners=False, linear) --
@@ -413,7 +413,7 @@ UC_HD void cone_point(const RayGeom& rg, const ConeInterval& ci, const ConeTable
 UC_HD uint32_t level_index(const GridLevel& lv, uint32_t x, uint32_t y, uint32_t z) {
     uint32_t idx;
     if (lv.hashed) idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
-    else idx = x + y * lv.stride1 + z * lv.stride1 * lv.stride1;
+    else idx = x + y * lv.stride1 + z * lv.stride2;
     // `index % hashmap_size` (gridencoder.cu:L83): hashed levels have power-of-two tables (AND mask); a dense
     // index of an in-range point is already < (res+1)^3 <= hashmap_size, so no reduction is needed there.
     // mod_mode: 0 = none, 1 = mask, 2 = generic modulo (non power-of-two hashed table).

@@ -40,147 +40,6 @@ int launch_resample(const ResampleParams& p, cudaStream_t st) {
 }
 
 // =================================================================================================
-// 2. sample + encode + density MLP: one thread per ray-sample
-//    render.cast_rays -> coord.contract -> GridEncoder -> erf pooling -> density_layer -> softplus
-// =================================================================================================
-constexpr int kSampleThreads = 128;
-
-template <int LMAX, bool NERF>
-__global__ void __launch_bounds__(kSampleThreads)
-sample_encode_kernel(const __grid_constant__ SampleParams p) {
-    __shared__ __align__(16) float sW1[64 * LMAX * 4];
-    __shared__ float sB1[64];
-    __shared__ float sW2[64];
-    for (int i = threadIdx.x; i < 64 * LMAX; i += kSampleThreads)
-        reinterpret_cast<float4*>(sW1)[i] = __ldg(reinterpret_cast<const float4*>(p.w1p) + i);
-    if (threadIdx.x < 64) {
-        sB1[threadIdx.x] = p.b1[threadIdx.x];
-        sW2[threadIdx.x] = p.w2[threadIdx.x];
-    }
-    __syncthreads();
-
-    const size_t total = (size_t)p.n_rays * p.S;
-    const size_t idx = (size_t)blockIdx.x * kSampleThreads + threadIdx.x;
-    if (idx >= total) return;
-    const uint32_t ray = (uint32_t)(idx / p.S);
-    const int s = (int)(idx - (size_t)ray * p.S);
-
-    RayGeom rg;
-    make_ray_geom(rg, p.rays.origins + 3 * (size_t)ray, p.rays.directions + 3 * (size_t)ray,
-                  p.rays.cam_dirs + 3 * (size_t)ray, p.rays.rand_vec + 3 * (size_t)ray, p.rays.radii[ray],
-                  p.rays.near[ray], p.rays.far[ray]);
-    const float s0 = p.sdist[(size_t)ray * (p.S + 1) + s];
-    const float s1 = p.sdist[(size_t)ray * (p.S + 1) + s + 1];
-    const float t0 = fa(fm(s0, rg.far), fm(fs(1.f, s0), rg.near));
-    const float t1 = fa(fm(s1, rg.far), fm(fs(1.f, s1), rg.near));
-    const ConeInterval ci = make_cone_interval(t0, t1);
-    const int odd = s & 1;
-    const int L = p.grid.num_levels;
-
-    float F[LMAX * 4];
-#pragma unroll
-    for (int i = 0; i < LMAX * 4; ++i) F[i] = 0.f;
-
-#pragma unroll 1
-    for (int j = 0; j < 6; ++j) {
-        float g[3], sigma;
-        cone_point(rg, ci, p.cone, j, odd, p.std_scale, g, sigma);
-        // gridencoder.cu:L110-135: out-of-range input -> zero features for every level
-        if (g[0] < 0.f || g[0] > 1.f || g[1] < 0.f || g[1] > 1.f || g[2] < 0.f || g[2] > 1.f) continue;
-        const float s8 = fm(8.f, fm(sigma, sigma));
-#pragma unroll
-        for (int l = 0; l < LMAX; ++l) {
-            if (l < L) {
-                const GridLevel& lv = p.grid.lv[l];
-                const CellCoords c = cell_of(lv, g);
-                const float4* tab = p.grid.table + lv.offset;
-                float4 v[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t ii = level_index(lv, c.ix + (k & 1), c.iy + ((k >> 1) & 1), c.iz + ((k >> 2) & 1));
-                    v[k] = ldg_f4(tab + ii);
-                }
-                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float w = ((k & 1) ? c.fx : 1 - c.fx) * ((k & 2) ? c.fy : 1 - c.fy) * ((k & 4) ? c.fz : 1 - c.fz);
-                    r.x = fmaf(w, v[k].x, r.x);
-                    r.y = fmaf(w, v[k].y, r.y);
-                    r.z = fmaf(w, v[k].z, r.z);
-                    r.w = fmaf(w, v[k].w, r.w);
-                }
-                // models.py:L495 scale-aware down-weighting erf(1/sqrt(8 std^2 G^2))
-                // (erf(x) rounds to exactly 1.0f for x >= 4: coarse levels skip the evaluation)
-                const float ea = rsqrtf(fm(s8, p.g2[l]));
-                const float om = ea >= 4.f ? 1.f : erff(ea);
-                F[4 * l + 0] = fmaf(om, r.x, F[4 * l + 0]);
-                F[4 * l + 1] = fmaf(om, r.y, F[4 * l + 1]);
-                F[4 * l + 2] = fmaf(om, r.z, F[4 * l + 2]);
-                F[4 * l + 3] = fmaf(om, r.w, F[4 * l + 3]);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < LMAX * 4; ++i) F[i] *= 0.16666667f;  // .mean(dim=-3) over the 6 points, models.py:L496
-
-    // density_layer: Linear(L*C,64) -> ReLU -> Linear(64, .)[0]   (models.py:L438-441, L507-508)
-    float raw = p.b2;
-    float* hrow = NERF ? p.h1 + idx * 64 : nullptr;
-#pragma unroll 4
-    for (int j = 0; j < 64; j += 4) {
-        float hv[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            float a = sB1[j + jj];
-            const float4* wr = reinterpret_cast<const float4*>(sW1) + (j + jj) * LMAX;
-#pragma unroll
-            for (int l = 0; l < LMAX; ++l) {
-                const float4 w = wr[l];
-                a = fmaf(w.x, F[4 * l + 0], a);
-                a = fmaf(w.y, F[4 * l + 1], a);
-                a = fmaf(w.z, F[4 * l + 2], a);
-                a = fmaf(w.w, F[4 * l + 3], a);
-            }
-            a = fmaxf(a, 0.f);
-            raw = fmaf(sW2[j + jj], a, raw);
-            hv[jj] = a;
-        }
-        if (NERF) *reinterpret_cast<float4*>(hrow + j) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-    }
-    p.density[idx] = softplus_f(raw + p.density_bias);  // models.py:L581
-}
-
-int sample_encode_lmax(int L) {
-    const int opts[] = {4, 6, 8, 10, 12, 16};
-    for (int o : opts)
-        if (L <= o) return o;
-    return 0;
-}
-
-template <int LMAX>
-static int launch_sample_t(const SampleParams& p, bool nerf, cudaStream_t st) {
-    const size_t total = (size_t)p.n_rays * p.S;
-    const unsigned blocks = (unsigned)div_up(total, (size_t)kSampleThreads);
-    if (nerf) sample_encode_kernel<LMAX, true><<<blocks, kSampleThreads, 0, st>>>(p);
-    else sample_encode_kernel<LMAX, false><<<blocks, kSampleThreads, 0, st>>>(p);
-    UC_LAUNCH_CHECK();
-    return 0;
-}
-
-int launch_sample_encode(const SampleParams& p, bool nerf, cudaStream_t st) {
-    if (p.n_rays == 0) return 0;
-    switch (sample_encode_lmax(p.grid.num_levels)) {
-        case 4: return launch_sample_t<4>(p, nerf, st);
-        case 6: return launch_sample_t<6>(p, nerf, st);
-        case 8: return launch_sample_t<8>(p, nerf, st);
-        case 10: return launch_sample_t<10>(p, nerf, st);
-        case 12: return launch_sample_t<12>(p, nerf, st);
-        case 16: return launch_sample_t<16>(p, nerf, st);
-        default: set_error("sample_encode: grid levels must be <= 16"); return 1;
-    }
-}
-
-// =================================================================================================
 // 3. colour MLP, fp32 SIMT path: 64-row tiles, register-tiled GEMM chain in shared memory.
 //    Reference (models.py:L587-674): x = W2 h1 + b2 ; in = [x, direnc] ; a = relu(V0 in + c0) ;
 //    a2 = relu(V1 [a, in] + c1) ; rgb = sigmoid(R a2 + r0) * (1 + 2 pad) - pad.  The bottleneck x has no

@@ -1,0 +1,218 @@
+// sample + encode + density MLP: one thread per ray-sample (the hash-gather kernel of the path).
+//   render.cast_rays -> coord.contract -> GridEncoder (6 points x L levels x 8 corners) -> erf pooling ->
+//   density_layer -> softplus          (models.py:L208-230, L485-512, L581; gridencoder.cu:L87-197)
+//
+// B200 notes (profiles/r1_*): the 128-bit gathers of one warp hit up to 32 different 128-byte lines per LDG, so
+// the kernel runs at the L1 wavefront limit (~1 line per clock per SM) with instruction issue as the second
+// limiter; DRAM traffic is far below the algorithmic gather bytes because the proposal table (101 MB) stays
+// L2-resident and the 6 multisample points / neighbouring samples share cells on the coarse levels.  Hence:
+//   * per-level code is specialised at compile time (dense index without modulo vs. XOR-prime hash + mask),
+//     corner indices are built from shared partial terms, all 8 gathers of a point-level are issued before use;
+//   * per-level constants come from the constant bank (__grid_constant__ params), weights of the 24/40 -> 64
+//     layer from shared memory as broadcast LDS.128;
+//   * blocks of 128 threads = 128 consecutive samples of (at most two) rays, so lanes of a warp touch
+//     neighbouring cells.
+#include "ray_march.cuh"
+
+namespace ucnerf {
+
+constexpr int kSampleThreads = 128;
+// resident CTAs per SM the register allocator is asked to allow (profiles/: occupancy vs. spills trade-off)
+#ifndef UC_MINB_SMALL
+#define UC_MINB_SMALL 6   // LMAX <= 6  -> 80 registers
+#endif
+#ifndef UC_MINB_LARGE
+#define UC_MINB_LARGE 5   // LMAX <= 10 -> 96 registers
+#endif
+
+// MODE: 0 dense (index < table size, no reduction), 1 hashed with power-of-two table, 2 generic (runtime flags)
+template <int MODE>
+__device__ __forceinline__ void gather8(const GridLevel& lv, const float4* __restrict__ tab, const CellCoords& c,
+                                        float4 (&v)[8]) {
+    if constexpr (MODE == 0) {
+        const uint32_t b00 = c.ix + c.iy * lv.stride1 + c.iz * lv.stride2;
+        const uint32_t b10 = b00 + lv.stride1, b01 = b00 + lv.stride2, b11 = b10 + lv.stride2;
+        v[0] = ldg_f4(tab + b00); v[1] = ldg_f4(tab + b00 + 1);
+        v[2] = ldg_f4(tab + b10); v[3] = ldg_f4(tab + b10 + 1);
+        v[4] = ldg_f4(tab + b01); v[5] = ldg_f4(tab + b01 + 1);
+        v[6] = ldg_f4(tab + b11); v[7] = ldg_f4(tab + b11 + 1);
+    } else if constexpr (MODE == 1) {
+        const uint32_t hy0 = c.iy * 2654435761u, hy1 = hy0 + 2654435761u;
+        const uint32_t hz0 = c.iz * 805459861u, hz1 = hz0 + 805459861u;
+        const uint32_t a00 = hy0 ^ hz0, a10 = hy1 ^ hz0, a01 = hy0 ^ hz1, a11 = hy1 ^ hz1;
+        const uint32_t x0 = c.ix, x1 = c.ix + 1, m = lv.pow2_mask;
+        v[0] = ldg_f4(tab + ((x0 ^ a00) & m)); v[1] = ldg_f4(tab + ((x1 ^ a00) & m));
+        v[2] = ldg_f4(tab + ((x0 ^ a10) & m)); v[3] = ldg_f4(tab + ((x1 ^ a10) & m));
+        v[4] = ldg_f4(tab + ((x0 ^ a01) & m)); v[5] = ldg_f4(tab + ((x1 ^ a01) & m));
+        v[6] = ldg_f4(tab + ((x0 ^ a11) & m)); v[7] = ldg_f4(tab + ((x1 ^ a11) & m));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            v[k] = ldg_f4(tab + level_index(lv, c.ix + (k & 1), c.iy + ((k >> 1) & 1), c.iz + ((k >> 2) & 1)));
+    }
+}
+
+// trilinear weights in the reference's association ((wx * wy) * wz), corner k: bit0 -> x, bit1 -> y, bit2 -> z
+__device__ __forceinline__ float4 interp8(const CellCoords& c, const float4 (&v)[8]) {
+    const float gx = 1 - c.fx, gy = 1 - c.fy, gz = 1 - c.fz;
+    const float w00 = gx * gy, w10 = c.fx * gy, w01 = gx * c.fy, w11 = c.fx * c.fy;
+    const float w[8] = {w00 * gz, w10 * gz, w01 * gz, w11 * gz, w00 * c.fz, w10 * c.fz, w01 * c.fz, w11 * c.fz};
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        r.x = fmaf(w[k], v[k].x, r.x);
+        r.y = fmaf(w[k], v[k].y, r.y);
+        r.z = fmaf(w[k], v[k].z, r.z);
+        r.w = fmaf(w[k], v[k].w, r.w);
+    }
+    return r;
+}
+
+// ND >= 0: levels [0, ND) are dense, levels >= ND hashed with power-of-two tables (compile-time specialisation);
+// ND < 0: decide per level at run time.
+template <int LMAX, bool NERF, int ND, int MINB>
+__global__ void __launch_bounds__(kSampleThreads, MINB)
+sample_encode_kernel(const __grid_constant__ SampleParams p) {
+    __shared__ __align__(16) float sW1[64 * LMAX * 4];
+    __shared__ float sB1[64];
+    __shared__ float sW2[64];
+    for (int i = threadIdx.x; i < 64 * LMAX; i += kSampleThreads)
+        reinterpret_cast<float4*>(sW1)[i] = __ldg(reinterpret_cast<const float4*>(p.w1p) + i);
+    if (threadIdx.x < 64) {
+        sB1[threadIdx.x] = p.b1[threadIdx.x];
+        sW2[threadIdx.x] = p.w2[threadIdx.x];
+    }
+    __syncthreads();
+
+    const size_t total = (size_t)p.n_rays * p.S;
+    const size_t idx = (size_t)blockIdx.x * kSampleThreads + threadIdx.x;
+    if (idx >= total) return;
+    const uint32_t ray = (uint32_t)(idx / p.S);
+    const int s = (int)(idx - (size_t)ray * p.S);
+
+    RayGeom rg;
+    make_ray_geom(rg, p.rays.origins + 3 * (size_t)ray, p.rays.directions + 3 * (size_t)ray,
+                  p.rays.cam_dirs + 3 * (size_t)ray, p.rays.rand_vec + 3 * (size_t)ray, p.rays.radii[ray],
+                  p.rays.near[ray], p.rays.far[ray]);
+    const float s0 = p.sdist[(size_t)ray * (p.S + 1) + s];
+    const float s1 = p.sdist[(size_t)ray * (p.S + 1) + s + 1];
+    const float t0 = fa(fm(s0, rg.far), fm(fs(1.f, s0), rg.near));
+    const float t1 = fa(fm(s1, rg.far), fm(fs(1.f, s1), rg.near));
+    const ConeInterval ci = make_cone_interval(t0, t1);
+    const int odd = s & 1;
+    const int L = p.grid.num_levels;
+
+    float F[LMAX * 4];
+#pragma unroll
+    for (int i = 0; i < LMAX * 4; ++i) F[i] = 0.f;
+
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) {
+        float g[3], sigma;
+        cone_point(rg, ci, p.cone, j, odd, p.std_scale, g, sigma);
+        // gridencoder.cu:L110-135: out-of-range input -> zero features for every level
+        if (g[0] < 0.f || g[0] > 1.f || g[1] < 0.f || g[1] > 1.f || g[2] < 0.f || g[2] > 1.f) continue;
+        const float s8 = fm(8.f, fm(sigma, sigma));
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) {
+            if (l < L) {
+                const GridLevel& lv = p.grid.lv[l];
+                const CellCoords c = cell_of(lv, g);
+                const float4* tab = p.grid.table + lv.offset;
+                float4 v[8];
+                if constexpr (ND >= 0) {
+                    if (l < ND) gather8<0>(lv, tab, c, v);
+                    else gather8<1>(lv, tab, c, v);
+                } else {
+                    gather8<2>(lv, tab, c, v);
+                }
+                const float4 r = interp8(c, v);
+                // models.py:L495 scale-aware down-weighting erf(1/sqrt(8 std^2 G^2));
+                // erf(x) rounds to exactly 1.0f for x >= 4, so coarse levels skip the evaluation
+                const float ea = rsqrtf(fm(s8, p.g2[l]));
+                const float om = ea >= 4.f ? 1.f : erff(ea);
+                F[4 * l + 0] = fmaf(om, r.x, F[4 * l + 0]);
+                F[4 * l + 1] = fmaf(om, r.y, F[4 * l + 1]);
+                F[4 * l + 2] = fmaf(om, r.z, F[4 * l + 2]);
+                F[4 * l + 3] = fmaf(om, r.w, F[4 * l + 3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < LMAX * 4; ++i) F[i] *= 0.16666667f;  // .mean(dim=-3) over the 6 points, models.py:L496
+
+    // density_layer: Linear(L*C,64) -> ReLU -> Linear(64, .)[0]   (models.py:L438-441, L507-508)
+    float raw = p.b2;
+    float* hrow = NERF ? p.h1 + idx * 64 : nullptr;
+#pragma unroll 4
+    for (int j = 0; j < 64; j += 4) {
+        float hv[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            float a = sB1[j + jj];
+            const float4* wr = reinterpret_cast<const float4*>(sW1) + (j + jj) * LMAX;
+#pragma unroll
+            for (int l = 0; l < LMAX; ++l) {
+                const float4 w = wr[l];
+                a = fmaf(w.x, F[4 * l + 0], a);
+                a = fmaf(w.y, F[4 * l + 1], a);
+                a = fmaf(w.z, F[4 * l + 2], a);
+                a = fmaf(w.w, F[4 * l + 3], a);
+            }
+            a = fmaxf(a, 0.f);
+            raw = fmaf(sW2[j + jj], a, raw);
+            hv[jj] = a;
+        }
+        if (NERF) *reinterpret_cast<float4*>(hrow + j) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    }
+    p.density[idx] = softplus_f(raw + p.density_bias);  // models.py:L581
+}
+
+int sample_encode_lmax(int L) {
+    const int opts[] = {4, 6, 8, 10, 16};
+    for (int o : opts)
+        if (L <= o) return o;
+    return 0;
+}
+
+// number of leading dense levels if the remaining ones are hashed with power-of-two tables, else -1
+static int dense_prefix(const GridDesc& g) {
+    int nd = 0;
+    while (nd < g.num_levels && !g.lv[nd].hashed) ++nd;
+    for (int l = nd; l < g.num_levels; ++l)
+        if (!g.lv[l].hashed || g.lv[l].mod_mode != 1) return -1;
+    return nd;
+}
+
+template <int LMAX, bool NERF, int ND, int MINB>
+static int launch_one(const SampleParams& p, cudaStream_t st) {
+    const size_t total = (size_t)p.n_rays * p.S;
+    const unsigned blocks = (unsigned)div_up(total, (size_t)kSampleThreads);
+    sample_encode_kernel<LMAX, NERF, ND, MINB><<<blocks, kSampleThreads, 0, st>>>(p);
+    UC_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int LMAX, int MINB>
+static int launch_lmax(const SampleParams& p, bool nerf, int nd, cudaStream_t st) {
+    if (nd == 3) return nerf ? launch_one<LMAX, true, 3, MINB>(p, st) : launch_one<LMAX, false, 3, MINB>(p, st);
+    if constexpr (LMAX == 4) {
+        if (nd == 1) return nerf ? launch_one<LMAX, true, 1, MINB>(p, st) : launch_one<LMAX, false, 1, MINB>(p, st);
+    }
+    return nerf ? launch_one<LMAX, true, -1, MINB>(p, st) : launch_one<LMAX, false, -1, MINB>(p, st);
+}
+
+int launch_sample_encode(const SampleParams& p, bool nerf, cudaStream_t st) {
+    if (p.n_rays == 0) return 0;
+    const int nd = dense_prefix(p.grid);
+    switch (sample_encode_lmax(p.grid.num_levels)) {
+        case 4: return launch_lmax<4, UC_MINB_SMALL>(p, nerf, nd, st);
+        case 6: return launch_lmax<6, UC_MINB_SMALL>(p, nerf, nd, st);
+        case 8: return launch_lmax<8, UC_MINB_LARGE>(p, nerf, nd, st);
+        case 10: return launch_lmax<10, UC_MINB_LARGE>(p, nerf, nd, st);
+        case 16: return launch_lmax<16, 3>(p, nerf, nd, st);
+        default: set_error("sample_encode: grid levels must be <= 16"); return 1;
+    }
+}
+
+}  // namespace ucnerf

@@ -247,18 +247,24 @@ def main():
         dom = max(fam_ms, key=fam_ms.get)
         shares = {k: round(v / max(sum(fam_ms.values()), 1e-9), 4) for k, v in fam_ms.items()}
         roofline = None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):   # per-launch DRAM bytes of that kernel from the committed ncu --set full capture
+            tj = json.load(open(tp))
+            if tj.get("workload") == wl.name and dom in tj and not args.chunk_rays:
+                traffic = tj[dom]["dram_bytes_read"] + tj[dom]["dram_bytes_write"]
         if dom in alg_bytes:
             bytes_total = alg_bytes[dom] * n * args.steps       # all launches of that family on this rank
             achieved = bytes_total / (fam_ms[dom] * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": f"sample_encode_kernel ({dom})", "achieved": achieved,
-                        "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                         "peak_source": how, "launches": fam[dom][1], "avg_launch_ms": fam_ms[dom] / max(fam[dom][1], 1),
                         "algorithmic_bytes_per_launch": bytes_total / max(fam[dom][1], 1)}
         else:
             flops = wl.mlp_flops_per_ray() * n * args.steps
             achieved = flops / (fam_ms[dom] * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                        "frac": achieved / tf_peak, "traffic": None, "peak_source": how, "launches": fam[dom][1],
+                        "frac": achieved / tf_peak, "traffic": traffic, "peak_source": how, "launches": fam[dom][1],
                         "avg_launch_ms": fam_ms[dom] / max(fam[dom][1], 1)}
         # all hash-gather kernels together (the BASELINE.md convention: whole-frame gather bytes / frame time)
         gather_gbs = wl.gather_bytes_per_ray() * n * args.steps / ((fam_ms["encode_prop"] + fam_ms["encode_nerf"]) * 1e-3) / 1e9

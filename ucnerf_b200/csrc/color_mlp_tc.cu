@@ -10,13 +10,14 @@
 // hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator keeps ~2^-21 relative error per product at 3 MMAs per
 // k-step, still ~5x the fp32 CUDA-core rate.
 //
-// CTA = one 128-row tile at a time (persistent over tiles), 6 warps:
-//   warps 0-3  producer / epilogue: thread t owns row t.  Builds the A operand chunk by chunk in shared memory
+// CTA = one 128-row tile at a time (persistent over tiles), 10 warps:
+//   warps 0-7  two producer / epilogue warpgroups (thread t of a group owns row t; group g fills A slot g, i.e.
+//              the chunks with c % 2 == g).  They build the A operand chunk by chunk in shared memory
 //              in the UMMA canonical K-major SWIZZLE_128B layout (hi tile + lo tile): from global h1 / the
 //              computed view-direction encoding, or from acc3 in TMEM (tcgen05.ld -> +bias -> relu -> split).
 //              Finally drains acc4, applies the rgb layer + sigmoid and writes the sample colours.
-//   warp 4     one elected thread issues tcgen05.mma (M=128, N=256, K=8, kind::tf32) and tcgen05.commit.
-//   warp 5     one elected thread streams the pre-swizzled weight chunks (hi|lo, 64 KB each) from L2 with
+//   warp 8     one elected thread issues tcgen05.mma (M=128, N=256, K=8, kind::tf32) and tcgen05.commit.
+//   warp 9     one elected thread streams the pre-swizzled weight chunks (hi|lo, 64 KB each) from L2 with
 //              cp.async.bulk (TMA bulk copy, completes on an mbarrier).
 // Pipelines: A ring (2 x 32 KB) and B ring (2 x 64 KB) with full/empty mbarriers; acc3/acc4 full/empty
 // mbarriers order MMA vs. TMEM drains.  TMEM: all 512 columns (acc3 = [0,256), acc4 = [256,512)).
@@ -47,16 +48,18 @@ constexpr uint32_t kOffC0 = 256;
 constexpr uint32_t kOffC1 = kOffC0 + 1024;
 constexpr uint32_t kOffR = kOffC1 + 1024;
 constexpr uint32_t kOffR0 = kOffR + 4096;
-constexpr uint32_t kMiscBytes = kOffR0 + 16;
+constexpr uint32_t kOffPart = kOffR0 + 16;          // [128] float4: rgb partial sums handed from group 1 to group 0
+constexpr uint32_t kMiscBytes = kOffPart + 2048;
 constexpr uint32_t kSmemTotal = kSmemMisc + kMiscBytes + 1024;  // +1024: manual 1 KB alignment slack
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                     // warps 0-3 / 4-7: producer groups, 8: MMA, 9: weight loader
+constexpr int kMmaWarp = 8;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
 // a/b K-major, N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
 enum Bar { A_FULL0 = 0, A_FULL1, A_EMPTY0, A_EMPTY1, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, ACC3_FULL, ACC4_FULL,
-           ACC3_EMPTY, ACC4_EMPTY, NUM_BARS };
+           ACC3_EMPTY, ACC4_EMPTY, PART_FULL, PART_EMPTY, NUM_BARS };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -184,6 +187,10 @@ using namespace tc;
 //   0: h1[0:32]  x P0   -> acc3 (init)      3: h1[0:32]  x P1 -> acc4 (init)     6..13: a[32j:32j+32] x V1a -> acc4
 //   1: h1[32:64] x P0   -> acc3             4: h1[32:64] x P1 -> acc4
 //   2: direnc    x P0   -> acc3, commit     5: direnc    x P1 -> acc4                  13: commit acc4
+// Producer warpgroup g (0/1) builds the chunks with (c & 1) == g into A slot g, so the two groups alternate and
+// each chunk's production overlaps the MMAs of the previous one.  The final epilogue of tile i (drain acc4, rgb
+// layer) is split by accumulator columns between the groups and is executed *after* each group has produced its
+// first chunk of tile i+1, so the tensor pipe already works on the next tile while acc4 is drained.
 __global__ void __launch_bounds__(kThreads, 1)
 color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -196,6 +203,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
     float* sC1 = reinterpret_cast<float*>(misc + kOffC1);
     float4* sR = reinterpret_cast<float4*>(misc + kOffR);
     float* sR0 = reinterpret_cast<float*>(misc + kOffR0);
+    float4* sPart = reinterpret_cast<float4*>(misc + kOffPart);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -211,10 +219,11 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         mbar_init(BAR(B_FULL0), 1); mbar_init(BAR(B_FULL1), 1);
         mbar_init(BAR(B_EMPTY0), 1); mbar_init(BAR(B_EMPTY1), 1);
         mbar_init(BAR(ACC3_FULL), 1); mbar_init(BAR(ACC4_FULL), 1);
-        mbar_init(BAR(ACC3_EMPTY), 128); mbar_init(BAR(ACC4_EMPTY), 128);
+        mbar_init(BAR(ACC3_EMPTY), 256); mbar_init(BAR(ACC4_EMPTY), 256);
+        mbar_init(BAR(PART_FULL), 128); mbar_init(BAR(PART_EMPTY), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {  // whole warp: allocate all 512 TMEM columns
+    if (warp == kMmaWarp) {  // whole warp: allocate all 512 TMEM columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(misc + kOffTmem)),
                      "r"(512)
                      : "memory");
@@ -227,11 +236,55 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
 
     const uint32_t ntiles = (p.n_rows + kTileM - 1) / kTileM;
 
-    if (warp < 4) {
-        // ================= producer / epilogue: thread t <-> row t of the tile =====================
-        const int t = threadIdx.x;
-        const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        uint32_t slot = 0, phase = 0, it = 0;
+    if (warp < 8) {
+        // ================= producer / epilogue warpgroups: thread <-> row t of the tile ================
+        const int g = warp >> 2;                 // warpgroup 0 / 1  == A slot it fills
+        const int t = threadIdx.x & 127;         // row inside the tile
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        uint8_t* my_slot = smem + kSmemA + g * kASlotBytes;
+        uint32_t k = 0;                          // chunks produced by this group so far (A_EMPTY phase)
+        uint32_t it = 0, prev_tile = 0;
+
+        // drain this group's half of acc4 for tile `tl` (iteration `itp`), rgb layer, sigmoid, store
+        auto final_epilogue = [&](uint32_t tl, uint32_t itp) -> bool {
+            if (!mbar_wait(BAR(ACC4_FULL), itp & 1, p.dbg, 3, ACC4_FULL, itp, 99)) return false;
+            tc_fence_after();
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll 1
+            for (int jj = 0; jj < 4; ++jj) {
+                const int col = g * 128 + 32 * jj;
+                uint32_t r[32];
+                tmem_ld32(lane_taddr + (uint32_t)(256 + col), r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float a2 = fmaxf(__uint_as_float(r[i]) + sC1[col + i], 0.f);
+                    const float4 w = sR[col + i];
+                    o0 = fmaf(a2, w.x, o0);
+                    o1 = fmaf(a2, w.y, o1);
+                    o2 = fmaf(a2, w.z, o2);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(BAR(ACC4_EMPTY));
+            if (g == 1) {
+                if (!mbar_wait(BAR(PART_EMPTY), (itp & 1) ^ 1, p.dbg, 9, PART_EMPTY, itp, 99)) return false;
+                sPart[t] = make_float4(o0, o1, o2, 0.f);
+                mbar_arrive(BAR(PART_FULL));
+            } else {
+                if (!mbar_wait(BAR(PART_FULL), itp & 1, p.dbg, 10, PART_FULL, itp, 99)) return false;
+                const float4 q = sPart[t];
+                mbar_arrive(BAR(PART_EMPTY));
+                const uint32_t row = tl * kTileM + t;
+                if (row < p.n_rows) {
+                    float* o = p.rgb + (size_t)row * 3;
+                    o[0] = fs(fm(sigmoid_f(o0 + q.x + sR0[0]), p.rgb_scale), p.rgb_padding);
+                    o[1] = fs(fm(sigmoid_f(o1 + q.y + sR0[1]), p.rgb_scale), p.rgb_padding);
+                    o[2] = fs(fm(sigmoid_f(o2 + q.z + sR0[2]), p.rgb_scale), p.rgb_padding);
+                }
+            }
+            return true;
+        };
+
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const uint32_t row = tile * kTileM + t;
             const bool valid = row < p.n_rows;
@@ -242,7 +295,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                 vd[0] = p.viewdirs[3 * (size_t)ray]; vd[1] = p.viewdirs[3 * (size_t)ray + 1]; vd[2] = p.viewdirs[3 * (size_t)ray + 2];
             }
 #pragma unroll 1
-            for (int c = 0; c < kSteps; ++c) {
+            for (int c = g; c < kSteps; c += 2) {
                 float v[32];
                 if (c == 0 || c == 1 || c == 3 || c == 4) {
                     const float4* src = reinterpret_cast<const float4*>(h1row + ((c == 0 || c == 3) ? 0 : 32));
@@ -267,7 +320,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                     }
                 } else {
                     const int j = c - 6;
-                    if (j == 0) {
+                    if (j < 2) {  // first TMEM chunk of this group for this tile
                         if (!mbar_wait(BAR(ACC3_FULL), it & 1, p.dbg, 1, ACC3_FULL, it, c)) goto teardown;
                         tc_fence_after();
                     }
@@ -275,45 +328,26 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                     tmem_ld32(lane_taddr + (uint32_t)(32 * j), r);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = fmaxf(__uint_as_float(r[i]) + sC0[32 * j + i], 0.f);
-                    if (j == 7) {  // acc3 fully drained: the MMA warp may overwrite it for the next tile
+                    if (j >= 6) {  // this group's part of acc3 is drained
                         tc_fence_before();
                         mbar_arrive(BAR(ACC3_EMPTY));
                     }
                 }
-                if (!mbar_wait(BAR(A_EMPTY0 + slot), phase ^ 1, p.dbg, 2, A_EMPTY0 + slot, it, c)) goto teardown;
-                store_a_row(smem + kSmemA + slot * kASlotBytes, t, v);
+                if (!mbar_wait(BAR(A_EMPTY0 + g), (k & 1) ^ 1, p.dbg, 2, A_EMPTY0 + g, it, c)) goto teardown;
+                store_a_row(my_slot, t, v);
                 fence_proxy_async();
-                mbar_arrive(BAR(A_FULL0 + slot));
-                slot ^= 1;
-                phase ^= (slot == 0);
-            }
-            // ---- final epilogue: a2 = relu(acc4 + c1'), rgb layer, sigmoid ----
-            if (!mbar_wait(BAR(ACC4_FULL), it & 1, p.dbg, 3, ACC4_FULL, it, 99)) goto teardown;
-            tc_fence_after();
-            float o0 = sR0[0], o1 = sR0[1], o2 = sR0[2];
-#pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-                uint32_t r[32];
-                tmem_ld32(lane_taddr + (uint32_t)(256 + 32 * j), r);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float a2 = fmaxf(__uint_as_float(r[i]) + sC1[32 * j + i], 0.f);
-                    const float4 w = sR[32 * j + i];
-                    o0 = fmaf(a2, w.x, o0);
-                    o1 = fmaf(a2, w.y, o1);
-                    o2 = fmaf(a2, w.z, o2);
+                mbar_arrive(BAR(A_FULL0 + g));
+                ++k;
+                if (c == g && it > 0) {
+                    if (!final_epilogue(prev_tile, it - 1)) goto teardown;
                 }
             }
-            tc_fence_before();
-            mbar_arrive(BAR(ACC4_EMPTY));
-            if (valid) {
-                float* o = p.rgb + (size_t)row * 3;
-                o[0] = fs(fm(sigmoid_f(o0), p.rgb_scale), p.rgb_padding);
-                o[1] = fs(fm(sigmoid_f(o1), p.rgb_scale), p.rgb_padding);
-                o[2] = fs(fm(sigmoid_f(o2), p.rgb_scale), p.rgb_padding);
-            }
+            prev_tile = tile;
         }
-    } else if (warp == 4) {
+        if (it > 0) {
+            if (!final_epilogue(prev_tile, it - 1)) goto teardown;
+        }
+    } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one thread) ==================================================
         if (lane == 0) {
             uint32_t slot = 0, phase = 0, it = 0;
@@ -369,7 +403,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
 teardown:
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }

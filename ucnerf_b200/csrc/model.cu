@@ -189,9 +189,10 @@ static int build_color(ucnerf_model* m) {
         double bacc = c0[n];
         for (int j = 0; j < BW; ++j) bacc += (double)vr[j] * (double)b2[j];
         c0p[n] = (float)bacc;
-        for (int k = 0; k < 64; ++k) {
+        for (int k = 0; k < 64; ++k) {  // h1 column k holds hidden unit h1_perm(k)
+            const int hu = h1_perm(k);
             double acc = 0.0;
-            for (int j = 0; j < BW; ++j) acc += (double)vr[j] * (double)w2[(size_t)j * 64 + k];
+            for (int j = 0; j < BW; ++j) acc += (double)vr[j] * (double)w2[(size_t)j * 64 + hu];
             p0t[(size_t)k * NP + n] = (float)acc;
         }
         for (int k = 0; k < ND; ++k) p0t[(size_t)(64 + k) * NP + n] = vr[BW + k];
@@ -204,8 +205,9 @@ static int build_color(ucnerf_model* m) {
         c1p[n] = (float)bacc;
         for (int k = 0; k < W; ++k) v1t[(size_t)k * NP + n] = src[k];
         for (int k = 0; k < 64; ++k) {
+            const int hu = h1_perm(k);
             double acc = 0.0;
-            for (int j = 0; j < BW; ++j) acc += (double)src[W + j] * (double)w2[(size_t)j * 64 + k];
+            for (int j = 0; j < BW; ++j) acc += (double)src[W + j] * (double)w2[(size_t)j * 64 + hu];
             v1t[(size_t)(NP + k) * NP + n] = (float)acc;
         }
         for (int k = 0; k < ND; ++k) v1t[(size_t)(NP + 64 + k) * NP + n] = src[W + BW + k];
@@ -309,6 +311,7 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
 
     const float* t_prev = nullptr;
     const float* w_prev = nullptr;
+    uint32_t t_prev_stride = 0;
     int n_prev = 1;
     double prod = 1.0;
     for (int li = 0; li < m->num_levels; ++li) {
@@ -317,9 +320,14 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         const int S = ls.S;
         float* sdist = o.sdist[li] ? o.sdist[li] + ray0 * (S + 1) : nullptr;
         float* weights = o.weights[li] ? o.weights[li] + ray0 * S : nullptr;
+        // The first level resamples sdist=[0,1], w=[1] (models.py:L143-147): its fenceposts are identical for every
+        // ray, so unless the caller wants them written out they are computed for ONE ray and shared (stride 0).
+        const bool shared_row = (li == 0 && sdist == nullptr);
+        uint32_t sdist_stride = (uint32_t)(S + 1);
         if (!sdist) {
-            if (int e = ls.sdist.ensure((size_t)n * (S + 1) * sizeof(float))) return e;
+            if (int e = ls.sdist.ensure((size_t)(shared_row ? 1 : n) * (S + 1) * sizeof(float))) return e;
             sdist = ls.sdist.as<float>();
+            if (shared_row) sdist_stride = 0;
         }
         if (!weights) {
             if (int e = ls.weights.ensure((size_t)n * S * sizeof(float))) return e;
@@ -331,7 +339,8 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         const bool use_dil = (d.dilation_bias > 0.0 || d.dilation_multiplier > 0.0) && li > 0;
 
         ResampleParams rs{};
-        rs.n_rays = n; rs.n_prev = n_prev; rs.t_prev = t_prev; rs.w_prev = w_prev; rs.dilate = use_dil ? 1 : 0;
+        rs.n_rays = shared_row ? 1u : n; rs.n_prev = n_prev; rs.t_prev = t_prev; rs.t_prev_stride = t_prev_stride;
+        rs.w_prev = w_prev; rs.dilate = use_dil ? 1 : 0;
         rs.dilation = dilation; rs.anneal = anneal; rs.padding = (float)d.resample_padding; rs.S = S;
         rs.u = ls.u.as<float>(); rs.out_sdist = sdist;
         if (int e = time_begin(m, st)) return e;
@@ -339,7 +348,8 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         if (int e = time_end(m, st, 0)) return e;
 
         SampleParams sp{};
-        sp.n_rays = n; sp.S = S; sp.rays = rp; sp.sdist = sdist; sp.grid = ls.grid; sp.cone = m->cone;
+        sp.n_rays = n; sp.S = S; sp.rays = rp; sp.sdist = sdist; sp.sdist_stride = sdist_stride; sp.grid = ls.grid;
+        sp.cone = m->cone;
         sp.std_scale = (float)d.std_scale; sp.density_bias = (float)d.density_bias;
         sp.w1p = ls.w1p.as<float>(); sp.b1 = ls.b1.as<float>(); sp.w2 = ls.w2.as<float>(); sp.b2 = ls.b2;
         sp.density = (nerf && o.sample_density) ? o.sample_density + ray0 * S : m->density.as<float>();
@@ -380,7 +390,8 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         }
 
         CompositeParams cq{};
-        cq.n_rays = n; cq.S = S; cq.sdist = sdist; cq.density = sp.density; cq.rgb = rgb_s; cq.rays = rp;
+        cq.n_rays = n; cq.S = S; cq.sdist = sdist; cq.sdist_stride = sdist_stride; cq.density = sp.density; cq.rgb = rgb_s;
+        cq.rays = rp;
         cq.bg = (float)d.bg_intensity; cq.extras = 1; cq.weights = weights;
         if (nerf) {
             cq.o_rgb = o.rgb ? o.rgb + 3 * ray0 : nullptr;
@@ -400,7 +411,7 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         if (int e = launch_composite(cq, st)) return e;
         if (int e = time_end(m, st, 4)) return e;
 
-        t_prev = sdist; w_prev = weights; n_prev = S;
+        t_prev = sdist; t_prev_stride = sdist_stride; w_prev = weights; n_prev = S;
     }
     return 0;
 }

@@ -19,7 +19,7 @@ resample_kernel(const ResampleParams p) {
     WarpExec ex{(int)(threadIdx.x & 31)};
     ResampleScratch sc;
     sc.carve(smem + (size_t)warp * ResampleScratch::floats(p.n_prev, p.S), p.n_prev, p.S);
-    const float* tprev = p.t_prev ? p.t_prev + (size_t)ray * (p.n_prev + 1) : nullptr;
+    const float* tprev = p.t_prev ? p.t_prev + (size_t)ray * p.t_prev_stride : nullptr;
     const float* wprev = p.w_prev ? p.w_prev + (size_t)ray * p.n_prev : nullptr;
     resample_ray(ex, p.n_prev, tprev, wprev, p.dilate != 0, p.dilation, p.anneal, p.padding, p.S, p.u, sc,
                  p.out_sdist + (size_t)ray * (p.S + 1));
@@ -254,7 +254,7 @@ composite_kernel(const CompositeParams p) {
     RayOutputs ro;
     const float dir[3] = {p.rays.directions[3 * (size_t)ray], p.rays.directions[3 * (size_t)ray + 1],
                           p.rays.directions[3 * (size_t)ray + 2]};
-    composite_ray(ex, p.S, p.sdist + (size_t)ray * (p.S + 1), p.density + (size_t)ray * p.S,
+    composite_ray(ex, p.S, p.sdist + (size_t)ray * p.sdist_stride, p.density + (size_t)ray * p.S,
                   p.rgb ? p.rgb + (size_t)ray * p.S * 3 : nullptr, dir, p.rays.near[ray], p.rays.far[ray], p.bg,
                   p.extras != 0, sc, p.weights + (size_t)ray * p.S, ro);
     if (ex.lane == 0) {

@@ -13,6 +13,7 @@ struct ResampleParams {
     uint32_t n_rays;
     int n_prev;              // bins of the previous level (1 for the first level)
     const float* t_prev;     // [N, n_prev+1] or NULL
+    uint32_t t_prev_stride;  // floats between rays (0: one row shared by all rays, e.g. the first level)
     const float* w_prev;     // [N, n_prev]   or NULL
     int dilate;
     float dilation, anneal, padding;
@@ -26,6 +27,7 @@ struct SampleParams {
     int S;
     RayPtrs rays;
     const float* sdist;      // [N, S+1]
+    uint32_t sdist_stride;   // floats between rays (0: shared row)
     GridDesc grid;
     ConeTable cone;
     float std_scale, density_bias;
@@ -73,6 +75,7 @@ struct CompositeParams {
     uint32_t n_rays;
     int S;
     const float* sdist;      // [N, S+1]
+    uint32_t sdist_stride;   // floats between rays (0: shared row)
     const float* density;    // [N, S]
     const float* rgb;        // [N, S, 3] or NULL
     RayPtrs rays;
@@ -91,6 +94,8 @@ int launch_color_mlp_tc(const ColorTcParams& p, cudaStream_t st);
 uint32_t color_tc_blob_bytes();
 int color_tc_status(uint32_t* out16);
 void color_tc_pack_chunk(const float* wt_rows, uint8_t* dst);
-int sample_encode_lmax(int L);  // padded level count used by the kernel instantiation (0 = unsupported)
+int sample_encode_lmax(int L);
+// h1 column c holds hidden unit kH1Perm(c) of density_layer.0 (layout written by sample_encode_kernel)
+inline int h1_perm(int c) { return (c / 16) + 4 * (c % 16); }  // padded level count used by the kernel instantiation (0 = unsupported)
 
 }  // namespace ucnerf

@@ -19,7 +19,10 @@ namespace ucnerf {
 constexpr int kSampleThreads = 128;
 // resident CTAs per SM the register allocator is asked to allow (profiles/: occupancy vs. spills trade-off)
 #ifndef UC_MINB_SMALL
-#define UC_MINB_SMALL 6   // LMAX <= 6  -> 80 registers
+#define UC_MINB_SMALL 5   // LMAX <= 6  -> 96 registers (6 -> 80 registers spills in the MLP phase)
+#endif
+#ifndef UC_REMAP_PROP
+#define UC_REMAP_PROP 1
 #endif
 #ifndef UC_MINB_LARGE
 #define UC_MINB_LARGE 5   // LMAX <= 10 -> 96 registers
@@ -70,102 +73,191 @@ __device__ __forceinline__ float4 interp8(const CellCoords& c, const float4 (&v)
 
 // ND >= 0: levels [0, ND) are dense, levels >= ND hashed with power-of-two tables (compile-time specialisation);
 // ND < 0: decide per level at run time.
-template <int LMAX, bool NERF, int ND, int MINB>
+//
+// Two phases per 128-sample CTA.  (1) gather: thread = sample, pooled features F[L*4] in registers, then parked in
+// shared memory.  (2) density layer: thread = (4 samples, 16 hidden units), so every weight fetched from shared
+// memory feeds 16 FMAs instead of 4 - the kernel is LSU-wavefront bound and the weight loads of a
+// thread-per-sample MLP were a quarter of all wavefronts.  Mappings are chosen bank-conflict free:
+// thread t: hg = t % 4 -> hidden units {hg + 4 jj}, sg = t / 4 -> samples {sg + 32 s}.  h1 is an internal buffer, so
+// it is stored in that permuted column order (column 16 hg + jj <-> hidden unit hg + 4 jj, see kH1Perm in
+// ray_march.cuh) and the consumer's weight rows are permuted to match on the host.
+template <int LMAX, bool NERF, int ND, int MINB, bool REMAP>
 __global__ void __launch_bounds__(kSampleThreads, MINB)
 sample_encode_kernel(const __grid_constant__ SampleParams p) {
-    __shared__ __align__(16) float sW1[64 * LMAX * 4];
-    __shared__ float sB1[64];
-    __shared__ float sW2[64];
-    for (int i = threadIdx.x; i < 64 * LMAX; i += kSampleThreads)
-        reinterpret_cast<float4*>(sW1)[i] = __ldg(reinterpret_cast<const float4*>(p.w1p) + i);
+    constexpr int LC = LMAX * 4;
+    constexpr int LDS = LC + 4;  // row stride (floats): 16-byte slots of 8 consecutive rows fall in distinct banks
+    extern __shared__ __align__(16) float smem_dyn[];
+    float* sW1 = smem_dyn;                       // [64][LDS]
+    float* sB1 = sW1 + 64 * LDS;                 // [64]
+    float* sW2 = sB1 + 64;                       // [64]
+    float* sF = sW2 + 64;                        // [128][LDS], only allocated for the re-mapped MLP phase
+    (void)sF;
+    for (int i = threadIdx.x; i < 64 * LMAX; i += kSampleThreads) {
+        const int j = i / LMAX, k4 = i - j * LMAX;
+        *reinterpret_cast<float4*>(sW1 + j * LDS + 4 * k4) = __ldg(reinterpret_cast<const float4*>(p.w1p) + i);
+    }
     if (threadIdx.x < 64) {
         sB1[threadIdx.x] = p.b1[threadIdx.x];
         sW2[threadIdx.x] = p.w2[threadIdx.x];
     }
-    __syncthreads();
 
     const size_t total = (size_t)p.n_rays * p.S;
-    const size_t idx = (size_t)blockIdx.x * kSampleThreads + threadIdx.x;
-    if (idx >= total) return;
-    const uint32_t ray = (uint32_t)(idx / p.S);
-    const int s = (int)(idx - (size_t)ray * p.S);
-
-    RayGeom rg;
-    make_ray_geom(rg, p.rays.origins + 3 * (size_t)ray, p.rays.directions + 3 * (size_t)ray,
-                  p.rays.cam_dirs + 3 * (size_t)ray, p.rays.rand_vec + 3 * (size_t)ray, p.rays.radii[ray],
-                  p.rays.near[ray], p.rays.far[ray]);
-    const float s0 = p.sdist[(size_t)ray * (p.S + 1) + s];
-    const float s1 = p.sdist[(size_t)ray * (p.S + 1) + s + 1];
-    const float t0 = fa(fm(s0, rg.far), fm(fs(1.f, s0), rg.near));
-    const float t1 = fa(fm(s1, rg.far), fm(fs(1.f, s1), rg.near));
-    const ConeInterval ci = make_cone_interval(t0, t1);
-    const int odd = s & 1;
-    const int L = p.grid.num_levels;
-
-    float F[LMAX * 4];
+    const size_t block0 = (size_t)blockIdx.x * kSampleThreads;
+    const size_t idx = block0 + threadIdx.x;
+    float F[LC];
 #pragma unroll
-    for (int i = 0; i < LMAX * 4; ++i) F[i] = 0.f;
+    for (int i = 0; i < LC; ++i) F[i] = 0.f;
 
+    if (idx < total) {
+        const uint32_t ray = (uint32_t)(idx / p.S);
+        const int s = (int)(idx - (size_t)ray * p.S);
+        RayGeom rg;
+        make_ray_geom(rg, p.rays.origins + 3 * (size_t)ray, p.rays.directions + 3 * (size_t)ray,
+                      p.rays.cam_dirs + 3 * (size_t)ray, p.rays.rand_vec + 3 * (size_t)ray, p.rays.radii[ray],
+                      p.rays.near[ray], p.rays.far[ray]);
+        const float s0 = p.sdist[(size_t)ray * p.sdist_stride + s];
+        const float s1 = p.sdist[(size_t)ray * p.sdist_stride + s + 1];
+        const float t0 = fa(fm(s0, rg.far), fm(fs(1.f, s0), rg.near));
+        const float t1 = fa(fm(s1, rg.far), fm(fs(1.f, s1), rg.near));
+        const ConeInterval ci = make_cone_interval(t0, t1);
+        const int odd = s & 1;
+        const int L = p.grid.num_levels;
 #pragma unroll 1
-    for (int j = 0; j < 6; ++j) {
-        float g[3], sigma;
-        cone_point(rg, ci, p.cone, j, odd, p.std_scale, g, sigma);
-        // gridencoder.cu:L110-135: out-of-range input -> zero features for every level
-        if (g[0] < 0.f || g[0] > 1.f || g[1] < 0.f || g[1] > 1.f || g[2] < 0.f || g[2] > 1.f) continue;
-        const float s8 = fm(8.f, fm(sigma, sigma));
-#pragma unroll
-        for (int l = 0; l < LMAX; ++l) {
-            if (l < L) {
-                const GridLevel& lv = p.grid.lv[l];
-                const CellCoords c = cell_of(lv, g);
-                const float4* tab = p.grid.table + lv.offset;
-                float4 v[8];
-                if constexpr (ND >= 0) {
-                    if (l < ND) gather8<0>(lv, tab, c, v);
-                    else gather8<1>(lv, tab, c, v);
-                } else {
-                    gather8<2>(lv, tab, c, v);
-                }
-                const float4 r = interp8(c, v);
-                // models.py:L495 scale-aware down-weighting erf(1/sqrt(8 std^2 G^2));
-                // erf(x) rounds to exactly 1.0f for x >= 4, so coarse levels skip the evaluation
-                const float ea = rsqrtf(fm(s8, p.g2[l]));
-                const float om = ea >= 4.f ? 1.f : erff(ea);
-                F[4 * l + 0] = fmaf(om, r.x, F[4 * l + 0]);
-                F[4 * l + 1] = fmaf(om, r.y, F[4 * l + 1]);
-                F[4 * l + 2] = fmaf(om, r.z, F[4 * l + 2]);
-                F[4 * l + 3] = fmaf(om, r.w, F[4 * l + 3]);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < LMAX * 4; ++i) F[i] *= 0.16666667f;  // .mean(dim=-3) over the 6 points, models.py:L496
-
-    // density_layer: Linear(L*C,64) -> ReLU -> Linear(64, .)[0]   (models.py:L438-441, L507-508)
-    float raw = p.b2;
-    float* hrow = NERF ? p.h1 + idx * 64 : nullptr;
-#pragma unroll 4
-    for (int j = 0; j < 64; j += 4) {
-        float hv[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            float a = sB1[j + jj];
-            const float4* wr = reinterpret_cast<const float4*>(sW1) + (j + jj) * LMAX;
+        for (int j = 0; j < 6; ++j) {
+            float g[3], sigma;
+            cone_point(rg, ci, p.cone, j, odd, p.std_scale, g, sigma);
+            // gridencoder.cu:L110-135: out-of-range input -> zero features for every level
+            if (g[0] < 0.f || g[0] > 1.f || g[1] < 0.f || g[1] > 1.f || g[2] < 0.f || g[2] > 1.f) continue;
+            const float s8 = fm(8.f, fm(sigma, sigma));
 #pragma unroll
             for (int l = 0; l < LMAX; ++l) {
-                const float4 w = wr[l];
-                a = fmaf(w.x, F[4 * l + 0], a);
-                a = fmaf(w.y, F[4 * l + 1], a);
-                a = fmaf(w.z, F[4 * l + 2], a);
-                a = fmaf(w.w, F[4 * l + 3], a);
+                if (l < L) {
+                    const GridLevel& lv = p.grid.lv[l];
+                    const CellCoords c = cell_of(lv, g);
+                    const float4* tab = p.grid.table + lv.offset;
+                    float4 v[8];
+                    if constexpr (ND >= 0) {
+                        if (l < ND) gather8<0>(lv, tab, c, v);
+                        else gather8<1>(lv, tab, c, v);
+                    } else {
+                        gather8<2>(lv, tab, c, v);
+                    }
+                    const float4 r = interp8(c, v);
+                    // models.py:L495 scale-aware down-weighting erf(1/sqrt(8 std^2 G^2));
+                    // erf(x) rounds to exactly 1.0f for x >= 4, so coarse levels skip the evaluation
+                    const float ea = rsqrtf(fm(s8, p.g2[l]));
+                    const float om = ea >= 4.f ? 1.f : erff(ea);
+                    F[4 * l + 0] = fmaf(om, r.x, F[4 * l + 0]);
+                    F[4 * l + 1] = fmaf(om, r.y, F[4 * l + 1]);
+                    F[4 * l + 2] = fmaf(om, r.z, F[4 * l + 2]);
+                    F[4 * l + 3] = fmaf(om, r.w, F[4 * l + 3]);
+                }
             }
-            a = fmaxf(a, 0.f);
-            raw = fmaf(sW2[j + jj], a, raw);
-            hv[jj] = a;
         }
-        if (NERF) *reinterpret_cast<float4*>(hrow + j) = make_float4(hv[0], hv[1], hv[2], hv[3]);
     }
-    p.density[idx] = softplus_f(raw + p.density_bias);  // models.py:L581
+    if constexpr (!REMAP) {
+        // thread-per-sample density layer (weights as broadcast LDS.128); used where the re-mapped phase does not pay
+        __syncthreads();  // weights staged
+        if (idx >= total) return;
+#pragma unroll
+        for (int i = 0; i < LC; ++i) F[i] *= 0.16666667f;  // .mean(dim=-3) over the 6 points, models.py:L496
+        float raw = p.b2;
+        float* hrow = NERF ? p.h1 + idx * 64 : nullptr;
+        const int hgp = 0;
+        (void)hgp;
+#pragma unroll 4
+        for (int c = 0; c < 64; c += 4) {  // h1 column c holds hidden unit h1_perm(c) (same layout as the re-mapped path)
+            float hv[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int j = ((c + cc) >> 4) + 4 * ((c + cc) & 15);
+                float a = sB1[j];
+                const float4* wr = reinterpret_cast<const float4*>(sW1 + j * LDS);
+#pragma unroll
+                for (int l = 0; l < LMAX; ++l) {
+                    const float4 w = wr[l];
+                    a = fmaf(w.x, F[4 * l + 0], a);
+                    a = fmaf(w.y, F[4 * l + 1], a);
+                    a = fmaf(w.z, F[4 * l + 2], a);
+                    a = fmaf(w.w, F[4 * l + 3], a);
+                }
+                a = fmaxf(a, 0.f);
+                raw = fmaf(sW2[j], a, raw);
+                hv[cc] = a;
+            }
+            if (NERF) *reinterpret_cast<float4*>(hrow + c) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        }
+        p.density[idx] = softplus_f(raw + p.density_bias);  // models.py:L581
+        return;
+    }
+    // .mean(dim=-3) over the 6 points (models.py:L496), parked in shared memory for the re-mapped MLP phase
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+        *reinterpret_cast<float4*>(sF + threadIdx.x * LDS + 4 * l) =
+            make_float4(F[4 * l] * 0.16666667f, F[4 * l + 1] * 0.16666667f, F[4 * l + 2] * 0.16666667f,
+                        F[4 * l + 3] * 0.16666667f);
+    __syncthreads();
+
+    // density_layer: Linear(L*C,64) -> ReLU -> Linear(64, .)[0]   (models.py:L438-441, L507-508)
+    const int hg = threadIdx.x & 3, sg = threadIdx.x >> 2;
+    float raw[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {  // 2 x 8 hidden units per thread keeps the accumulators at 32 registers
+        float acc[4][8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float b = sB1[hg + 4 * (8 * half + jj)];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) acc[s][jj] = b;
+        }
+#pragma unroll 2
+        for (int k4 = 0; k4 < LMAX; ++k4) {
+            float4 f[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) f[s] = *reinterpret_cast<const float4*>(sF + (sg + 32 * s) * LDS + 4 * k4);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float4 w = *reinterpret_cast<const float4*>(sW1 + (hg + 4 * (8 * half + jj)) * LDS + 4 * k4);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    acc[s][jj] = fmaf(w.x, f[s].x, acc[s][jj]);
+                    acc[s][jj] = fmaf(w.y, f[s].y, acc[s][jj]);
+                    acc[s][jj] = fmaf(w.z, f[s].z, acc[s][jj]);
+                    acc[s][jj] = fmaf(w.w, f[s].w, acc[s][jj]);
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float w2 = sW2[hg + 4 * (8 * half + jj)];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                acc[s][jj] = fmaxf(acc[s][jj], 0.f);
+                raw[s] = fmaf(w2, acc[s][jj], raw[s]);
+            }
+        }
+        if (NERF) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const size_t row = block0 + (size_t)(sg + 32 * s);
+                if (row < total) {
+                    float* hrow = p.h1 + row * 64 + 16 * hg + 8 * half;  // permuted column order, see above
+                    *reinterpret_cast<float4*>(hrow) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+                    *reinterpret_cast<float4*>(hrow + 4) = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        raw[s] += __shfl_xor_sync(0xffffffffu, raw[s], 1);
+        raw[s] += __shfl_xor_sync(0xffffffffu, raw[s], 2);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const size_t row = block0 + (size_t)(sg + 32 * s);
+        if (row < total && hg == s) p.density[row] = softplus_f(raw[s] + p.b2 + p.density_bias);  // models.py:L581
+    }
 }
 
 int sample_encode_lmax(int L) {
@@ -185,13 +277,27 @@ static int dense_prefix(const GridDesc& g) {
 }
 
 template <int LMAX, bool NERF, int ND, int MINB>
-static int launch_one(const SampleParams& p, cudaStream_t st) {
+static int launch_one_impl(const SampleParams& p, cudaStream_t st) {
     const size_t total = (size_t)p.n_rays * p.S;
     const unsigned blocks = (unsigned)div_up(total, (size_t)kSampleThreads);
-    sample_encode_kernel<LMAX, NERF, ND, MINB><<<blocks, kSampleThreads, 0, st>>>(p);
+    // measured on B200 (profiles/r1_summary.md): the re-mapped density layer pays on the proposal level only
+    constexpr bool kRemap = UC_REMAP_PROP ? !NERF : false;
+    constexpr size_t smem = sizeof(float) * ((64 + (kRemap ? kSampleThreads : 0)) * (LMAX * 4 + 4) + 128);
+    if constexpr (smem > 48 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            UC_CUDA_OK(cudaFuncSetAttribute(sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+    }
+    sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap><<<blocks, kSampleThreads, smem, st>>>(p);
     UC_LAUNCH_CHECK();
     return 0;
 }
+
+template <int LMAX, bool NERF, int ND, int MINB>
+static int launch_one(const SampleParams& p, cudaStream_t st) { return launch_one_impl<LMAX, NERF, ND, MINB>(p, st); }
 
 template <int LMAX, int MINB>
 static int launch_lmax(const SampleParams& p, bool nerf, int nd, cudaStream_t st) {

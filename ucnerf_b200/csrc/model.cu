@@ -74,7 +74,7 @@ struct ucnerf_model {
     DevBuf density, h1, rgb_s;
     // host-entry staging
     DevBuf stage_in, stage_out;
-    int64_t chunk_rays = 65536;
+    int64_t chunk_rays = 131072;
     int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 3xTF32 (error if shapes unsupported), 2 = auto
     bool timing = false;
     float ms[5] = {0, 0, 0, 0, 0};

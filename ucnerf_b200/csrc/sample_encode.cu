@@ -71,6 +71,26 @@ __device__ __forceinline__ float4 interp8(const CellCoords& c, const float4 (&v)
     return r;
 }
 
+// Work mapping: a warp = 32 CONSECUTIVE RAYS at the SAME sample index (position q -> ray group q / (32 S), sample
+// (q / 32) % S, ray-in-group q % 32).  Neighbouring pixels' rays are a fraction of a cell apart on most levels, so
+// the 32 lanes of one gather instruction fall into a handful of 128-byte lines instead of 32 different ones (the
+// kernel is bound by L1 wavefronts = distinct lines per instruction).  For unordered ray batches this is merely
+// as slow as any other mapping.  Row index of (ray, s) in the [N*S] buffers stays ray * S + s.
+struct SamplePos {
+    uint32_t ray;
+    int s;
+    bool valid;
+};
+__device__ __forceinline__ SamplePos sample_pos(size_t q, uint32_t n_rays, int S) {
+    const size_t group = q / ((size_t)32 * S);
+    const uint32_t rem = (uint32_t)(q - group * (size_t)32 * S);
+    SamplePos sp;
+    sp.ray = (uint32_t)group * 32u + (rem & 31u);
+    sp.s = (int)(rem >> 5);
+    sp.valid = sp.ray < n_rays;
+    return sp;
+}
+
 // ND >= 0: levels [0, ND) are dense, levels >= ND hashed with power-of-two tables (compile-time specialisation);
 // ND < 0: decide per level at run time.
 //
@@ -101,16 +121,16 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
         sW2[threadIdx.x] = p.w2[threadIdx.x];
     }
 
-    const size_t total = (size_t)p.n_rays * p.S;
     const size_t block0 = (size_t)blockIdx.x * kSampleThreads;
-    const size_t idx = block0 + threadIdx.x;
+    const SamplePos me = sample_pos(block0 + threadIdx.x, p.n_rays, p.S);
+    const size_t idx = (size_t)me.ray * p.S + me.s;  // row of this sample in the [N*S] buffers
     float F[LC];
 #pragma unroll
     for (int i = 0; i < LC; ++i) F[i] = 0.f;
 
-    if (idx < total) {
-        const uint32_t ray = (uint32_t)(idx / p.S);
-        const int s = (int)(idx - (size_t)ray * p.S);
+    if (me.valid) {
+        const uint32_t ray = me.ray;
+        const int s = me.s;
         RayGeom rg;
         make_ray_geom(rg, p.rays.origins + 3 * (size_t)ray, p.rays.directions + 3 * (size_t)ray,
                       p.rays.cam_dirs + 3 * (size_t)ray, p.rays.rand_vec + 3 * (size_t)ray, p.rays.radii[ray],
@@ -158,7 +178,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
     if constexpr (!REMAP) {
         // thread-per-sample density layer (weights as broadcast LDS.128); used where the re-mapped phase does not pay
         __syncthreads();  // weights staged
-        if (idx >= total) return;
+        if (!me.valid) return;
 #pragma unroll
         for (int i = 0; i < LC; ++i) F[i] *= 0.16666667f;  // .mean(dim=-3) over the 6 points, models.py:L496
         float raw = p.b2;
@@ -239,9 +259,9 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
         if (NERF) {
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                const size_t row = block0 + (size_t)(sg + 32 * s);
-                if (row < total) {
-                    float* hrow = p.h1 + row * 64 + 16 * hg + 8 * half;  // permuted column order, see above
+                const SamplePos o = sample_pos(block0 + (size_t)(sg + 32 * s), p.n_rays, p.S);
+                if (o.valid) {
+                    float* hrow = p.h1 + ((size_t)o.ray * p.S + o.s) * 64 + 16 * hg + 8 * half;  // permuted columns
                     *reinterpret_cast<float4*>(hrow) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
                     *reinterpret_cast<float4*>(hrow + 4) = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
                 }
@@ -255,8 +275,8 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
     }
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const size_t row = block0 + (size_t)(sg + 32 * s);
-        if (row < total && hg == s) p.density[row] = softplus_f(raw[s] + p.b2 + p.density_bias);  // models.py:L581
+        const SamplePos o = sample_pos(block0 + (size_t)(sg + 32 * s), p.n_rays, p.S);
+        if (o.valid && hg == s) p.density[(size_t)o.ray * p.S + o.s] = softplus_f(raw[s] + p.b2 + p.density_bias);  // models.py:L581
     }
 }
 
@@ -278,7 +298,7 @@ static int dense_prefix(const GridDesc& g) {
 
 template <int LMAX, bool NERF, int ND, int MINB>
 static int launch_one_impl(const SampleParams& p, cudaStream_t st) {
-    const size_t total = (size_t)p.n_rays * p.S;
+    const size_t total = (size_t)div_up(p.n_rays, 32u) * 32u * (size_t)p.S;  // ray groups of 32, see sample_pos
     const unsigned blocks = (unsigned)div_up(total, (size_t)kSampleThreads);
     // measured on B200 (profiles/r1_summary.md): the re-mapped density layer pays on the proposal level only
     constexpr bool kRemap = UC_REMAP_PROP ? !NERF : false;

@@ -54,6 +54,25 @@ __device__ __forceinline__ float4 ldg_f4(const float4* p) {
 }
 #endif
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2): two IEEE fp32 operations per issue slot -------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    ra = *reinterpret_cast<unsigned long long*>(&a);
+    rb = *reinterpret_cast<unsigned long long*>(&b);
+    rc = *reinterpret_cast<unsigned long long*>(&c);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    ra = *reinterpret_cast<unsigned long long*>(&a);
+    rb = *reinterpret_cast<unsigned long long*>(&b);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+#endif
+
 // ---- per-level geometry of a hash grid, precomputed on the host for the fused path -----------
 struct GridLevel {
     uint32_t offset;        // entry offset of the level inside `embeddings`

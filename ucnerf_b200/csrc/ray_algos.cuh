@@ -387,9 +387,11 @@ UC_HD void cone_point(const RayGeom& rg, const ConeInterval& ci, const ConeTable
                       float (&g)[3], float& sigma) {
     const float t = fa(ci.t0, fm(ci.tdA, fa(ci.B, fm(ct.tcoef[j], ci.Cq))));
     const float rt = fm(rg.radius, t);
-    const float px = fd(fm(rt, ct.cosv[odd][j]), 1.41421356237f);
-    const float py = fd(fm(rt, ct.sinv[odd][j]), 1.41421356237f);
-    float sd = fd(fm(fm(std_scale, rg.radius), t), 1.41421356237f);
+    // the lateral offsets (|px|,|py| ~ 1e-4 t) and the std only need relative accuracy ~1e-7: multiply by 1/sqrt(2)
+    // instead of the reference's IEEE division (changes the rounding of x by < 1e-4 ulp on average)
+    const float px = fm(fm(rt, ct.cosv[odd][j]), 0.70710678118f);
+    const float py = fm(fm(rt, ct.sinv[odd][j]), 0.70710678118f);
+    float sd = fm(fm(fm(std_scale, rg.radius), t), 0.70710678118f);
     float x[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -400,7 +402,13 @@ UC_HD void cone_point(const RayGeom& rg, const ConeInterval& ci, const ConeTable
         const float k = fd(fs(fm(2.f, mag), 1.f), m2);
 #pragma unroll
         for (int i = 0; i < 3; ++i) x[i] = fm(k, x[i]);
-        const float c = fd(powf(fs(fm(2.f, mag), 1.f), 0.33333334f), mag);
+        // coord.py:L68 (pow(2|x|-1, 1/3) / |x|)^2: cbrtf + fast division are within 2 ulp of the torch result, and the
+        // std only enters through erf(1/(sqrt(8) std G))
+#if defined(__CUDA_ARCH__)
+        const float c = __fdividef(cbrtf(fs(fm(2.f, mag), 1.f)), mag);
+#else
+        const float c = fd(cbrtf(fs(fm(2.f, mag), 1.f)), mag);
+#endif
         sd = fm(fm(c, c), sd);
     }
     sigma = fm(sd, 0.5f);

@@ -25,7 +25,7 @@ constexpr int kSampleThreads = 128;
 #define UC_REMAP_PROP 1
 #endif
 #ifndef UC_MINB_LARGE
-#define UC_MINB_LARGE 5   // LMAX <= 10 -> 96 registers
+#define UC_MINB_LARGE 4   // LMAX <= 10 -> 128 registers (5 -> 96 registers spills with FFMA2 register pairs; measured slower)
 #endif
 
 // MODE: 0 dense (index < table size, no reduction), 1 hashed with power-of-two table, 2 generic (runtime flags)
@@ -55,18 +55,25 @@ __device__ __forceinline__ void gather8(const GridLevel& lv, const float4* __res
     }
 }
 
-// trilinear weights in the reference's association ((wx * wy) * wz), corner k: bit0 -> x, bit1 -> y, bit2 -> z
-__device__ __forceinline__ float4 interp8(const CellCoords& c, const float4 (&v)[8]) {
-    const float gx = 1 - c.fx, gy = 1 - c.fy, gz = 1 - c.fz;
-    const float w00 = gx * gy, w10 = c.fx * gy, w01 = gx * c.fy, w11 = c.fx * c.fy;
-    const float w[8] = {w00 * gz, w10 * gz, w01 * gz, w11 * gz, w00 * c.fz, w10 * c.fz, w01 * c.fz, w11 * c.fz};
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+// trilinear weights in the reference's association ((wx * wy) * wz), corner k: bit0 -> x, bit1 -> y, bit2 -> z.
+// Packed fp32x2 math (FFMA2/FMUL2): every weight is computed as a duplicated pair {w, w} so the four channels of a
+// corner take two fused multiply-adds; element-wise results are bit-identical to the scalar sequence.
+struct Feat4 {
+    float2 xy, zw;
+};
+__device__ __forceinline__ Feat4 interp8(const CellCoords& c, const float4 (&v)[8]) {
+    const float2 fx = make_float2(c.fx, c.fx), fy = make_float2(c.fy, c.fy), fz = make_float2(c.fz, c.fz);
+    const float2 gx = make_float2(1 - c.fx, 1 - c.fx), gy = make_float2(1 - c.fy, 1 - c.fy), gz = make_float2(1 - c.fz, 1 - c.fz);
+    const float2 w00 = fmul2(gx, gy), w10 = fmul2(fx, gy), w01 = fmul2(gx, fy), w11 = fmul2(fx, fy);
+    const float2 w[8] = {fmul2(w00, gz), fmul2(w10, gz), fmul2(w01, gz), fmul2(w11, gz),
+                         fmul2(w00, fz), fmul2(w10, fz), fmul2(w01, fz), fmul2(w11, fz)};
+    Feat4 r;
+    r.xy = make_float2(0.f, 0.f);
+    r.zw = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        r.x = fmaf(w[k], v[k].x, r.x);
-        r.y = fmaf(w[k], v[k].y, r.y);
-        r.z = fmaf(w[k], v[k].z, r.z);
-        r.w = fmaf(w[k], v[k].w, r.w);
+        r.xy = ffma2(w[k], make_float2(v[k].x, v[k].y), r.xy);
+        r.zw = ffma2(w[k], make_float2(v[k].z, v[k].w), r.zw);
     }
     return r;
 }
@@ -124,9 +131,9 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
     const size_t block0 = (size_t)blockIdx.x * kSampleThreads;
     const SamplePos me = sample_pos(block0 + threadIdx.x, p.n_rays, p.S);
     const size_t idx = (size_t)me.ray * p.S + me.s;  // row of this sample in the [N*S] buffers
-    float F[LC];
+    float2 F2[LMAX * 2];  // pooled features, (x,y) / (z,w) pairs per level
 #pragma unroll
-    for (int i = 0; i < LC; ++i) F[i] = 0.f;
+    for (int i = 0; i < LMAX * 2; ++i) F2[i] = make_float2(0.f, 0.f);
 
     if (me.valid) {
         const uint32_t ray = me.ray;
@@ -162,15 +169,14 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
                     } else {
                         gather8<2>(lv, tab, c, v);
                     }
-                    const float4 r = interp8(c, v);
+                    const Feat4 r = interp8(c, v);
                     // models.py:L495 scale-aware down-weighting erf(1/sqrt(8 std^2 G^2));
                     // erf(x) rounds to exactly 1.0f for x >= 4, so coarse levels skip the evaluation
                     const float ea = rsqrtf(fm(s8, p.g2[l]));
                     const float om = ea >= 4.f ? 1.f : erff(ea);
-                    F[4 * l + 0] = fmaf(om, r.x, F[4 * l + 0]);
-                    F[4 * l + 1] = fmaf(om, r.y, F[4 * l + 1]);
-                    F[4 * l + 2] = fmaf(om, r.z, F[4 * l + 2]);
-                    F[4 * l + 3] = fmaf(om, r.w, F[4 * l + 3]);
+                    const float2 om2 = make_float2(om, om);
+                    F2[2 * l] = ffma2(om2, r.xy, F2[2 * l]);
+                    F2[2 * l + 1] = ffma2(om2, r.zw, F2[2 * l + 1]);
                 }
             }
         }
@@ -179,29 +185,26 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
         // thread-per-sample density layer (weights as broadcast LDS.128); used where the re-mapped phase does not pay
         __syncthreads();  // weights staged
         if (!me.valid) return;
+        const float2 sixth = make_float2(0.16666667f, 0.16666667f);
 #pragma unroll
-        for (int i = 0; i < LC; ++i) F[i] *= 0.16666667f;  // .mean(dim=-3) over the 6 points, models.py:L496
+        for (int i = 0; i < LMAX * 2; ++i) F2[i] = fmul2(F2[i], sixth);  // .mean(dim=-3) over the 6 points, models.py:L496
         float raw = p.b2;
         float* hrow = NERF ? p.h1 + idx * 64 : nullptr;
-        const int hgp = 0;
-        (void)hgp;
 #pragma unroll 4
         for (int c = 0; c < 64; c += 4) {  // h1 column c holds hidden unit h1_perm(c) (same layout as the re-mapped path)
             float hv[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 const int j = ((c + cc) >> 4) + 4 * ((c + cc) & 15);
-                float a = sB1[j];
+                float2 a2 = make_float2(sB1[j], 0.f);  // even / odd partial sums (FFMA2)
                 const float4* wr = reinterpret_cast<const float4*>(sW1 + j * LDS);
 #pragma unroll
                 for (int l = 0; l < LMAX; ++l) {
                     const float4 w = wr[l];
-                    a = fmaf(w.x, F[4 * l + 0], a);
-                    a = fmaf(w.y, F[4 * l + 1], a);
-                    a = fmaf(w.z, F[4 * l + 2], a);
-                    a = fmaf(w.w, F[4 * l + 3], a);
+                    a2 = ffma2(make_float2(w.x, w.y), F2[2 * l], a2);
+                    a2 = ffma2(make_float2(w.z, w.w), F2[2 * l + 1], a2);
                 }
-                a = fmaxf(a, 0.f);
+                const float a = fmaxf(a2.x + a2.y, 0.f);
                 raw = fmaf(sW2[j], a, raw);
                 hv[cc] = a;
             }
@@ -214,8 +217,8 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
 #pragma unroll
     for (int l = 0; l < LMAX; ++l)
         *reinterpret_cast<float4*>(sF + threadIdx.x * LDS + 4 * l) =
-            make_float4(F[4 * l] * 0.16666667f, F[4 * l + 1] * 0.16666667f, F[4 * l + 2] * 0.16666667f,
-                        F[4 * l + 3] * 0.16666667f);
+            make_float4(F2[2 * l].x * 0.16666667f, F2[2 * l].y * 0.16666667f, F2[2 * l + 1].x * 0.16666667f,
+                        F2[2 * l + 1].y * 0.16666667f);
     __syncthreads();
 
     // density_layer: Linear(L*C,64) -> ReLU -> Linear(64, .)[0]   (models.py:L438-441, L507-508)
@@ -223,12 +226,12 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
     float raw[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {  // 2 x 8 hidden units per thread keeps the accumulators at 32 registers
-        float acc[4][8];
+        float2 acc2[4][8];  // (even-k, odd-k) partial sums per (sample, hidden unit): FFMA2
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
             const float b = sB1[hg + 4 * (8 * half + jj)];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) acc[s][jj] = b;
+            for (int s = 0; s < 4; ++s) acc2[s][jj] = make_float2(b, 0.f);
         }
 #pragma unroll 2
         for (int k4 = 0; k4 < LMAX; ++k4) {
@@ -238,21 +241,21 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 const float4 w = *reinterpret_cast<const float4*>(sW1 + (hg + 4 * (8 * half + jj)) * LDS + 4 * k4);
+                const float2 wxy = make_float2(w.x, w.y), wzw = make_float2(w.z, w.w);
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    acc[s][jj] = fmaf(w.x, f[s].x, acc[s][jj]);
-                    acc[s][jj] = fmaf(w.y, f[s].y, acc[s][jj]);
-                    acc[s][jj] = fmaf(w.z, f[s].z, acc[s][jj]);
-                    acc[s][jj] = fmaf(w.w, f[s].w, acc[s][jj]);
+                    acc2[s][jj] = ffma2(wxy, make_float2(f[s].x, f[s].y), acc2[s][jj]);
+                    acc2[s][jj] = ffma2(wzw, make_float2(f[s].z, f[s].w), acc2[s][jj]);
                 }
             }
         }
+        float acc[4][8];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
             const float w2 = sW2[hg + 4 * (8 * half + jj)];
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                acc[s][jj] = fmaxf(acc[s][jj], 0.f);
+                acc[s][jj] = fmaxf(acc2[s][jj].x + acc2[s][jj].y, 0.f);
                 raw[s] = fmaf(w2, acc[s][jj], raw[s]);
             }
         }

@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--chunk-rays", type=int, default=0)
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc-debug", type=int, default=0, help="profiling experiment flags for the TC kernel (invalid results)")
     return ap.parse_args()
 
 
@@ -168,6 +169,8 @@ def main():
     r = synthetic.make_renderer(wl, sd, dev)
     if args.chunk_rays:
         r.set_option("chunk_rays", args.chunk_rays)
+    if args.tc_debug:
+        r.set_option("tc_debug", args.tc_debug)
     rays_h = synthetic.pinhole_rays(wl.height, wl.width, seed=rank)   # every rank renders its own camera
     n = rays_h["origins"].shape[0]
     rays_d = {k: v.to(dev) for k, v in rays_h.items()}

@@ -16,7 +16,7 @@ simt = run(r, batch)
 print("simt done", flush=True)
 r.set_option("color_mlp", 1)
 tc = run(r, batch)
-st = (ctypes.c_uint32 * 16)()
+st = (ctypes.c_uint32 * 32)()
 lib.ucnerf_debug_tc_status(st)
 print("watchdog:", list(st)[:8], flush=True)
 d = np.abs(tc["sample_rgb"] - simt["sample_rgb"])

@@ -32,7 +32,7 @@ namespace tc {
 constexpr int kTileM = 128;
 constexpr int kN = 256;
 constexpr int kKC = 32;                       // K elements per chunk = one 128-byte swizzle row
-constexpr int kSteps = 14;                    // chunks per tile (see kStep* below)
+constexpr int kSteps = 12;                    // chunks per tile (see the step table below)
 constexpr uint32_t kATileBytes = kTileM * kKC * 4;   // 16 KB (one of hi / lo)
 constexpr uint32_t kASlotBytes = 2 * kATileBytes;    // 32 KB
 constexpr uint32_t kBTileBytes = kN * kKC * 4;       // 32 KB
@@ -156,6 +156,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -183,10 +196,12 @@ __device__ __forceinline__ void store_a_row(uint8_t* slot, int row, const float 
 
 using namespace tc;
 
-// Step table of one tile (A chunk source, weight chunk = step index in the blob, accumulator):
-//   0: h1[0:32]  x P0   -> acc3 (init)      3: h1[0:32]  x P1 -> acc4 (init)     6..13: a[32j:32j+32] x V1a -> acc4
-//   1: h1[32:64] x P0   -> acc3             4: h1[32:64] x P1 -> acc4
-//   2: direnc    x P0   -> acc3, commit     5: direnc    x P1 -> acc4                  13: commit acc4
+// Step table of one tile (A chunk source x weight chunk = step index in the blob -> accumulator):
+//   0: h1[0:32]  x P0 -> acc3 (init)     2: h1[0:32]  x P1 -> acc4 (init)     4..11: a[32j:32j+32] x V1a -> acc4
+//   1: h1[32:64] x P0 -> acc3, commit    3: h1[32:64] x P1 -> acc4                   11: commit acc4
+// The view-direction encoding is constant per ray, so its contribution (P0d direnc + c0', P1d direnc + c1') is
+// evaluated once per ray by dir_bias_kernel (fp32 FMAs) and added as a per-ray bias when the accumulators are
+// drained: two of fourteen MMA steps and all sinf() evaluations leave this kernel.
 // Producer warpgroup g (0/1) builds the chunks with (c & 1) == g into A slot g, so the two groups alternate and
 // each chunk's production overlaps the MMAs of the previous one.  The final epilogue of tile i (drain acc4, rgb
 // layer) is split by accumulator columns between the groups and is executed *after* each group has produced its
@@ -199,8 +214,6 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
     const uint32_t bar0 = smem_u32(misc + kOffBar);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(misc + kOffTmem);
-    float* sC0 = reinterpret_cast<float*>(misc + kOffC0);
-    float* sC1 = reinterpret_cast<float*>(misc + kOffC1);
     float4* sR = reinterpret_cast<float4*>(misc + kOffR);
     float* sR0 = reinterpret_cast<float*>(misc + kOffR0);
     float4* sPart = reinterpret_cast<float4*>(misc + kOffPart);
@@ -208,8 +221,6 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < 256; i += kThreads) {
-        sC0[i] = p.c0[i];
-        sC1[i] = p.c1[i];
         sR[i] = reinterpret_cast<const float4*>(p.rt)[i];
     }
     if (threadIdx.x < 4) sR0[threadIdx.x] = p.r0[threadIdx.x];
@@ -244,24 +255,44 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         uint8_t* my_slot = smem + kSmemA + g * kASlotBytes;
         uint32_t k = 0;                          // chunks produced by this group so far (A_EMPTY phase)
         uint32_t it = 0, prev_tile = 0;
+        // profiling (debug_flags bit 2): thread 0 of each group in CTA 0 -> dbg[16 + 8 g ...]: total, waits on
+        // A_EMPTY / ACC3_FULL / ACC4_FULL+PART, time in h1 chunks / dir chunks / tmem chunks (kilo-cycles)
+        const bool prof = (p.debug_flags & 4u) != 0 && t == 0 && blockIdx.x == 0;
+        long long pw_aempty = 0, pw_acc3 = 0, pw_epi = 0, pt_h1 = 0, pt_dir = 0, pt_tm = 0;
+        const long long pt_begin = clock64();
 
         // drain this group's half of acc4 for tile `tl` (iteration `itp`), rgb layer, sigmoid, store
         auto final_epilogue = [&](uint32_t tl, uint32_t itp) -> bool {
             if (!mbar_wait(BAR(ACC4_FULL), itp & 1, p.dbg, 3, ACC4_FULL, itp, 99)) return false;
             tc_fence_after();
             float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-#pragma unroll 1
-            for (int jj = 0; jj < 4; ++jj) {
-                const int col = g * 128 + 32 * jj;
-                uint32_t r[32];
-                tmem_ld32(lane_taddr + (uint32_t)(256 + col), r);
+            const uint32_t erow = tl * kTileM + t;
+            const float4* bias1 = reinterpret_cast<const float4*>(
+                p.dir_bias + (size_t)((erow < p.n_rows ? erow : 0u) / (uint32_t)p.S) * 512 + 256 + g * 128);
+            // software pipeline: the TMEM load of the next 32 columns is in flight while the current ones are consumed
+            uint32_t ra[32], rb[32];
+            tmem_ld32_issue(lane_taddr + (uint32_t)(256 + g * 128), ra);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float a2 = fmaxf(__uint_as_float(r[i]) + sC1[col + i], 0.f);
-                    const float4 w = sR[col + i];
-                    o0 = fmaf(a2, w.x, o0);
-                    o1 = fmaf(a2, w.y, o1);
-                    o2 = fmaf(a2, w.z, o2);
+            for (int jj = 0; jj < 4; ++jj) {
+                float4 bb[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) bb[q] = __ldg(bias1 + 8 * jj + q);
+                tmem_ld_wait();
+                uint32_t (&cur)[32] = (jj & 1) ? rb : ra;
+                uint32_t (&nxt)[32] = (jj & 1) ? ra : rb;
+                if (jj < 3) tmem_ld32_issue(lane_taddr + (uint32_t)(256 + g * 128 + 32 * (jj + 1)), nxt);
+                const int col = g * 128 + 32 * jj;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float bq[4] = {bb[q].x, bb[q].y, bb[q].z, bb[q].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float a2 = fmaxf(__uint_as_float(cur[4 * q + e]) + bq[e], 0.f);
+                        const float4 w = sR[col + 4 * q + e];
+                        o0 = fmaf(a2, w.x, o0);
+                        o1 = fmaf(a2, w.y, o1);
+                        o2 = fmaf(a2, w.z, o2);
+                    }
                 }
             }
             tc_fence_before();
@@ -289,57 +320,67 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
             const uint32_t row = tile * kTileM + t;
             const bool valid = row < p.n_rows;
             const float* h1row = p.h1 + (size_t)(valid ? row : 0) * 64;
-            float vd[3] = {0.f, 0.f, 0.f};
-            if (valid) {
-                const uint32_t ray = row / (uint32_t)p.S;
-                vd[0] = p.viewdirs[3 * (size_t)ray]; vd[1] = p.viewdirs[3 * (size_t)ray + 1]; vd[2] = p.viewdirs[3 * (size_t)ray + 2];
-            }
+            const float* bias0 = p.dir_bias + (size_t)((valid ? row : 0u) / (uint32_t)p.S) * 512;  // per-ray [c0' | c1'] rows
+            float hkeep[32];
 #pragma unroll 1
             for (int c = g; c < kSteps; c += 2) {
                 float v[32];
-                if (c == 0 || c == 1 || c == 3 || c == 4) {
-                    const float4* src = reinterpret_cast<const float4*>(h1row + ((c == 0 || c == 3) ? 0 : 32));
+                const long long tc0 = prof ? clock64() : 0;
+                long long tw = 0;
+                if (c < 2) {  // this group's half of the h1 row: loaded once, kept in registers for chunk c + 2
+                    const float4* src = reinterpret_cast<const float4*>(h1row + 32 * g);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         float4 x = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                        hkeep[4 * q] = x.x; hkeep[4 * q + 1] = x.y; hkeep[4 * q + 2] = x.z; hkeep[4 * q + 3] = x.w;
                     }
-                } else if (c == 2 || c == 5) {  // coord.py:L214-225 pos_enc(viewdirs, 0, 4) -> 27 values, zero padded
+                }
+                if (c < 4) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-                    if (valid) {
-                        v[0] = vd[0]; v[1] = vd[1]; v[2] = vd[2];
-#pragma unroll
-                        for (int d = 0; d < 4; ++d)
-#pragma unroll
-                            for (int ax = 0; ax < 3; ++ax) {
-                                const float x = fm(vd[ax], (float)(1 << d));
-                                v[3 + 3 * d + ax] = sinf(x);
-                                v[15 + 3 * d + ax] = sinf(fa(x, 1.57079637f));
-                            }
-                    }
+                    for (int i = 0; i < 32; ++i) v[i] = hkeep[i];
                 } else {
-                    const int j = c - 6;
+                    const int j = c - 4;
                     if (j < 2) {  // first TMEM chunk of this group for this tile
+                        const long long ta = prof ? clock64() : 0;
                         if (!mbar_wait(BAR(ACC3_FULL), it & 1, p.dbg, 1, ACC3_FULL, it, c)) goto teardown;
+                        if (prof) { tw = clock64() - ta; pw_acc3 += tw; }
                         tc_fence_after();
                     }
                     uint32_t r[32];
-                    tmem_ld32(lane_taddr + (uint32_t)(32 * j), r);
+                    tmem_ld32_issue(lane_taddr + (uint32_t)(32 * j), r);
+                    const float4* b0 = reinterpret_cast<const float4*>(bias0 + 32 * j);
+                    float4 bb[8];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(__uint_as_float(r[i]) + sC0[32 * j + i], 0.f);
+                    for (int q = 0; q < 8; ++q) bb[q] = __ldg(b0 + q);  // overlaps the TMEM load
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        v[4 * q] = fmaxf(__uint_as_float(r[4 * q]) + bb[q].x, 0.f);
+                        v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + bb[q].y, 0.f);
+                        v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + bb[q].z, 0.f);
+                        v[4 * q + 3] = fmaxf(__uint_as_float(r[4 * q + 3]) + bb[q].w, 0.f);
+                    }
                     if (j >= 6) {  // this group's part of acc3 is drained
                         tc_fence_before();
                         mbar_arrive(BAR(ACC3_EMPTY));
                     }
                 }
+                const long long tb = prof ? clock64() : 0;
                 if (!mbar_wait(BAR(A_EMPTY0 + g), (k & 1) ^ 1, p.dbg, 2, A_EMPTY0 + g, it, c)) goto teardown;
-                store_a_row(my_slot, t, v);
+                const long long tb2 = prof ? clock64() : 0;
+                if (prof) { pw_aempty += tb2 - tb; tw += tb2 - tb; }
+                if (!(p.debug_flags & 2u)) store_a_row(my_slot, t, v);  // bit 1: profiling experiment, skip A stores
                 fence_proxy_async();
                 mbar_arrive(BAR(A_FULL0 + g));
                 ++k;
+                if (prof) {
+                    const long long work = clock64() - tc0 - tw;
+                    if (c < 4) pt_h1 += work; else pt_tm += work;
+                }
                 if (c == g && it > 0) {
+                    const long long te = prof ? clock64() : 0;
                     if (!final_epilogue(prev_tile, it - 1)) goto teardown;
+                    if (prof) pw_epi += clock64() - te;
                 }
             }
             prev_tile = tile;
@@ -347,24 +388,38 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         if (it > 0) {
             if (!final_epilogue(prev_tile, it - 1)) goto teardown;
         }
+        if (prof) {
+            uint32_t* d = p.dbg + 16 + 8 * g;
+            d[0] = (uint32_t)((clock64() - pt_begin) >> 10); d[1] = (uint32_t)(pw_aempty >> 10); d[2] = (uint32_t)(pw_acc3 >> 10);
+            d[3] = (uint32_t)(pw_epi >> 10); d[4] = (uint32_t)(pt_h1 >> 10); d[5] = (uint32_t)(pt_dir >> 10); d[6] = (uint32_t)(pt_tm >> 10);
+        }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one thread) ==================================================
         if (lane == 0) {
             uint32_t slot = 0, phase = 0, it = 0;
+            // profiling (debug_flags bit 2): cycles this thread spent waiting per barrier kind, CTA 0 -> dbg[8..12]
+            const bool prof = (p.debug_flags & 4u) != 0;
+            long long w_acc3 = 0, w_acc4 = 0, w_b = 0, w_a = 0;
+            const long long t_begin = clock64();
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
 #pragma unroll 1
                 for (int s = 0; s < kSteps; ++s) {
+                    long long t0 = prof ? clock64() : 0;
                     if (s == 0 && !mbar_wait(BAR(ACC3_EMPTY), (it & 1) ^ 1, p.dbg, 4, ACC3_EMPTY, it, s)) goto teardown;
-                    if (s == 3 && !mbar_wait(BAR(ACC4_EMPTY), (it & 1) ^ 1, p.dbg, 5, ACC4_EMPTY, it, s)) goto teardown;
+                    if (prof) { const long long t1 = clock64(); w_acc3 += t1 - t0; t0 = t1; }
+                    if (s == 2 && !mbar_wait(BAR(ACC4_EMPTY), (it & 1) ^ 1, p.dbg, 5, ACC4_EMPTY, it, s)) goto teardown;
+                    if (prof) { const long long t1 = clock64(); w_acc4 += t1 - t0; t0 = t1; }
                     if (!mbar_wait(BAR(B_FULL0 + slot), phase, p.dbg, 6, B_FULL0 + slot, it, s)) goto teardown;
+                    if (prof) { const long long t1 = clock64(); w_b += t1 - t0; t0 = t1; }
                     if (!mbar_wait(BAR(A_FULL0 + slot), phase, p.dbg, 7, A_FULL0 + slot, it, s)) goto teardown;
+                    if (prof) { const long long t1 = clock64(); w_a += t1 - t0; t0 = t1; }
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + kSmemA + slot * kASlotBytes);
                     const uint32_t a_lo = a_hi + kATileBytes;
                     const uint32_t b_hi = smem_u32(smem + kSmemB + slot * kBSlotBytes);
                     const uint32_t b_lo = b_hi + kBTileBytes;
-                    const uint32_t acc = tmem_base + (s < 3 ? 0u : 256u);
-                    const bool init = (s == 0 || s == 3);
+                    const uint32_t acc = tmem_base + (s < 2 ? 0u : 256u);
+                    const bool init = (s == 0 || s == 2);
 #pragma unroll
                     for (int ks = 0; ks < kKC / 8; ++ks) {
                         const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
@@ -375,11 +430,16 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                     }
                     umma_commit(BAR(A_EMPTY0 + slot));
                     umma_commit(BAR(B_EMPTY0 + slot));
-                    if (s == 2) umma_commit(BAR(ACC3_FULL));
+                    if (s == 1) umma_commit(BAR(ACC3_FULL));
                     if (s == kSteps - 1) umma_commit(BAR(ACC4_FULL));
                     slot ^= 1;
                     phase ^= (slot == 0);
                 }
+            }
+            if (prof && blockIdx.x == 0) {
+                p.dbg[8] = (uint32_t)((clock64() - t_begin) >> 10);
+                p.dbg[9] = (uint32_t)(w_acc3 >> 10); p.dbg[10] = (uint32_t)(w_acc4 >> 10);
+                p.dbg[11] = (uint32_t)(w_b >> 10); p.dbg[12] = (uint32_t)(w_a >> 10); p.dbg[13] = it;
             }
         }
     } else {
@@ -390,9 +450,13 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
 #pragma unroll 1
                 for (int s = 0; s < kSteps; ++s) {
                     if (!mbar_wait(BAR(B_EMPTY0 + slot), phase ^ 1, p.dbg, 8, B_EMPTY0 + slot, it, s)) goto teardown;
-                    mbar_expect_tx(BAR(B_FULL0 + slot), kBSlotBytes);
-                    bulk_g2s(smem_u32(smem + kSmemB + slot * kBSlotBytes), p.wblob + (size_t)s * kBSlotBytes, kBSlotBytes,
-                             BAR(B_FULL0 + slot));
+                    if (p.debug_flags & 1u) {  // profiling experiment: no weight traffic (results are garbage)
+                        mbar_arrive(BAR(B_FULL0 + slot));
+                    } else {
+                        mbar_expect_tx(BAR(B_FULL0 + slot), kBSlotBytes);
+                        bulk_g2s(smem_u32(smem + kSmemB + slot * kBSlotBytes), p.wblob + (size_t)s * kBSlotBytes,
+                                 kBSlotBytes, BAR(B_FULL0 + slot));
+                    }
                     slot ^= 1;
                     phase ^= (slot == 0);
                 }
@@ -409,21 +473,73 @@ teardown:
     }
 }
 
-static uint32_t* g_tc_dbg = nullptr;   // [16] words: watchdog record of color_mlp_tc_kernel (0 = healthy)
+// Per-ray constant part of both colour layers: out[ray][0:256] = c0' + P0d direnc(viewdir), out[ray][256:512] =
+// c1' + P1d direnc(viewdir), direnc = pos_enc(viewdirs, 0, 4) (coord.py:L214-225, 27 values).  fp32 FMAs.
+__global__ void __launch_bounds__(256)
+dir_bias_kernel(const float* __restrict__ viewdirs, const float* __restrict__ wdir /* [2][32][256] */,
+                const float* __restrict__ c0, const float* __restrict__ c1, float* __restrict__ out, uint32_t n_rays) {
+    __shared__ float enc[8][32];
+    const uint32_t ray0 = blockIdx.x * 8;
+    if (threadIdx.x < 8 * 32) {
+        const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+        float val = 0.f;
+        if (ray0 + r < n_rays && c < 27) {
+            const float* vd = viewdirs + 3 * (size_t)(ray0 + r);
+            if (c < 3) {
+                val = vd[c];
+            } else {
+                const int q = c - 3, qq = q < 12 ? q : q - 12, deg = qq / 3, ax = qq - 3 * deg;
+                float x = fm(vd[ax], (float)(1 << deg));
+                if (q >= 12) x = fa(x, 1.57079637f);
+                val = sinf(x);
+            }
+        }
+        enc[r][c] = val;
+    }
+    __syncthreads();
+    const int n = threadIdx.x;
+    float w0[27], w1[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        w0[k] = __ldg(wdir + (size_t)k * 256 + n);
+        w1[k] = __ldg(wdir + (size_t)(32 + k) * 256 + n);
+    }
+    const float b0 = c0[n], b1 = c1[n];
+    for (int r = 0; r < 8 && ray0 + r < n_rays; ++r) {
+        float a0 = b0, a1 = b1;
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+            a0 = fmaf(w0[k], enc[r][k], a0);
+            a1 = fmaf(w1[k], enc[r][k], a1);
+        }
+        out[(size_t)(ray0 + r) * 512 + n] = a0;
+        out[(size_t)(ray0 + r) * 512 + 256 + n] = a1;
+    }
+}
+
+int launch_dir_bias(const float* viewdirs, const float* wdir, const float* c0, const float* c1, float* out,
+                    uint32_t n_rays, cudaStream_t st) {
+    if (n_rays == 0) return 0;
+    dir_bias_kernel<<<div_up(n_rays, 8u), 256, 0, st>>>(viewdirs, wdir, c0, c1, out, n_rays);
+    UC_LAUNCH_CHECK();
+    return 0;
+}
+
+static uint32_t* g_tc_dbg = nullptr;   // [32] words: watchdog record of color_mlp_tc_kernel (0 = healthy)
 
 int color_tc_status(uint32_t* out16) {
-    for (int i = 0; i < 16; ++i) out16[i] = 0;
+    for (int i = 0; i < 32; ++i) out16[i] = 0;
     if (!g_tc_dbg) return 0;
     UC_CUDA_OK(cudaDeviceSynchronize());
-    UC_CUDA_OK(cudaMemcpy(out16, g_tc_dbg, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    UC_CUDA_OK(cudaMemcpy(out16, g_tc_dbg, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 
 int launch_color_mlp_tc(const ColorTcParams& p_in, cudaStream_t st) {
     if (p_in.n_rows == 0) return 0;
     if (!g_tc_dbg) {
-        UC_CUDA_OK(cudaMalloc(&g_tc_dbg, 16 * sizeof(uint32_t)));
-        UC_CUDA_OK(cudaMemset(g_tc_dbg, 0, 16 * sizeof(uint32_t)));
+        UC_CUDA_OK(cudaMalloc(&g_tc_dbg, 32 * sizeof(uint32_t)));
+        UC_CUDA_OK(cudaMemset(g_tc_dbg, 0, 32 * sizeof(uint32_t)));
     }
     ColorTcParams p = p_in;
     p.dbg = g_tc_dbg;

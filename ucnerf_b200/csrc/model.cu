@@ -69,7 +69,8 @@ struct ucnerf_model {
     LevelState lv[UCNERF_MAX_PROP_LEVELS + 1];
     ConeTable cone;
     int np = 0;  // padded colour-MLP width
-    DevBuf w2t, b2, v0t, c0, v1t, c1, rt, r0, wblob;
+    DevBuf w2t, b2, v0t, c0, v1t, c1, rt, r0, wblob, wdir, dir_bias;
+    uint32_t tc_debug = 0;
     bool tc_ok = false;   // tensor-core colour MLP available for these shapes (W = 256, deg_view = 4)
     DevBuf density, h1, rgb_s;
     // host-entry staging
@@ -222,10 +223,18 @@ static int build_color(ucnerf_model* m) {
     if (m->tc_ok) {
         // step order of color_mlp_tc_kernel: P0 rows [h1 0:32, h1 32:64, dir], P1 rows [h1 0:32, h1 32:64, dir], V1a x8
         std::vector<uint8_t> blob(color_tc_blob_bytes());
-        const size_t cb = blob.size() / 14;
-        for (int s = 0; s < 3; ++s) color_tc_pack_chunk(&p0t[(size_t)(32 * s) * NP], blob.data() + cb * s);
-        for (int s = 0; s < 3; ++s) color_tc_pack_chunk(&v1t[(size_t)(NP + 32 * s) * NP], blob.data() + cb * (3 + s));
-        for (int j = 0; j < 8; ++j) color_tc_pack_chunk(&v1t[(size_t)(32 * j) * NP], blob.data() + cb * (6 + j));
+        const size_t cb = blob.size() / 12;
+        for (int s = 0; s < 2; ++s) color_tc_pack_chunk(&p0t[(size_t)(32 * s) * NP], blob.data() + cb * s);
+        for (int s = 0; s < 2; ++s) color_tc_pack_chunk(&v1t[(size_t)(NP + 32 * s) * NP], blob.data() + cb * (2 + s));
+        for (int j = 0; j < 8; ++j) color_tc_pack_chunk(&v1t[(size_t)(32 * j) * NP], blob.data() + cb * (4 + j));
+        // view-direction rows of both layers for dir_bias_kernel: [2][32][256]
+        std::vector<float> wd((size_t)2 * 32 * 256, 0.f);
+        for (int k = 0; k < 32; ++k)
+            for (int n = 0; n < 256; ++n) {
+                wd[(size_t)k * 256 + n] = p0t[(size_t)(64 + k) * NP + n];
+                wd[(size_t)(32 + k) * 256 + n] = v1t[(size_t)(NP + 64 + k) * NP + n];
+            }
+        if (int e = upload(m->wdir, wd)) return e;
         if (int e = m->wblob.ensure(blob.size())) return e;
         UC_CUDA_OK(cudaMemcpy(m->wblob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     }
@@ -380,8 +389,10 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
                 UC_REQUIRE(m->tc_ok, "color_mlp=1 (tensor core) needs net_width_viewdirs/bottleneck <= 256 padded to 256 and deg_view == 4");
                 ColorTcParams tp{};
                 tp.n_rows = cp.n_rows; tp.S = S; tp.h1 = cp.h1; tp.viewdirs = cp.viewdirs;
-                tp.wblob = m->wblob.as<uint8_t>(); tp.c0 = cp.c0; tp.c1 = cp.c1; tp.rt = cp.rt; tp.r0 = cp.r0;
-                tp.rgb_scale = cp.rgb_scale; tp.rgb_padding = cp.rgb_padding; tp.rgb = cp.rgb;
+                if (int e = m->dir_bias.ensure((size_t)n * 512 * sizeof(float))) return e;
+                if (int e = launch_dir_bias(rp.viewdirs, m->wdir.as<float>(), cp.c0, cp.c1, m->dir_bias.as<float>(), n, st)) return e;
+                tp.wblob = m->wblob.as<uint8_t>(); tp.dir_bias = m->dir_bias.as<float>(); tp.rt = cp.rt; tp.r0 = cp.r0;
+                tp.rgb_scale = cp.rgb_scale; tp.rgb_padding = cp.rgb_padding; tp.rgb = cp.rgb; tp.debug_flags = m->tc_debug;
                 if (int e = launch_color_mlp_tc(tp, st)) return e;
             } else {
                 if (int e = launch_color_mlp_simt(cp, m->np, st)) return e;
@@ -449,7 +460,7 @@ extern "C" int ucnerf_model_destroy(ucnerf_model* m) {
     if (!m) return 0;
     for (auto& ls : m->lv) { ls.w1p.release(); ls.b1.release(); ls.w2.release(); ls.u.release(); ls.sdist.release(); ls.weights.release(); }
     for (DevBuf* b : {&m->w2t, &m->b2, &m->v0t, &m->c0, &m->v1t, &m->c1, &m->rt, &m->r0, &m->density, &m->h1, &m->rgb_s,
-                      &m->stage_in, &m->stage_out, &m->wblob})
+                      &m->stage_in, &m->stage_out, &m->wblob, &m->wdir, &m->dir_bias})
         b->release();
     resolve_timing(m);
     for (auto& e : m->pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -463,6 +474,7 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
     if (k == "chunk_rays") { UC_REQUIRE(value >= 1, "chunk_rays must be >= 1"); m->chunk_rays = value; }
     else if (k == "color_mlp") { UC_REQUIRE(value >= 0 && value <= 2, "color_mlp: 0 = fp32 SIMT, 1 = tensor core, 2 = auto"); m->color_mode = (int)value; }
     else if (k == "timing") m->timing = value != 0;
+    else if (k == "tc_debug") m->tc_debug = (uint32_t)value;  // profiling experiments (results invalid when != 0)
     else { set_error("set_option: unknown key " + k); return 1; }
     return 0;
 }
@@ -545,7 +557,7 @@ extern "C" int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const u
         UC_CUDA_OK(cudaMemcpyAsync(s.host, *s.dev_field, s.floats * sizeof(float), cudaMemcpyDeviceToHost, st));
     UC_CUDA_OK(cudaStreamSynchronize(st));
     {
-        uint32_t wd[16];
+        uint32_t wd[32];
         if (int e = color_tc_status(wd)) return e;
         if (wd[0] != 0) {
             set_error("color_mlp_tc: pipeline watchdog fired (tag " + std::to_string(wd[0]) + ", barrier " +

@@ -63,12 +63,13 @@ struct ColorTcParams {
     int S;
     const float* h1;         // [rows, 64]
     const float* viewdirs;   // [N, 3]
-    const uint8_t* wblob;    // 14 chunks x (hi tile | lo tile) in UMMA K-major SWIZZLE_128B layout
-    const float *c0, *c1;    // [256] folded biases
+    const uint8_t* wblob;    // 12 chunks x (hi tile | lo tile) in UMMA K-major SWIZZLE_128B layout
+    const float* dir_bias;   // [N rays][512]: per-ray biases of both layers (dir_bias_kernel)
     const float *rt, *r0;    // [256][4], [4]
     float rgb_scale, rgb_padding;
     float* rgb;              // [rows, 3]
     uint32_t* dbg;           // watchdog record (set by the launcher)
+    uint32_t debug_flags;    // profiling experiments only (ucnerf_set_option "tc_debug"); 0 in production
 };
 
 struct CompositeParams {
@@ -93,6 +94,8 @@ int launch_composite(const CompositeParams& p, cudaStream_t st);
 int launch_color_mlp_tc(const ColorTcParams& p, cudaStream_t st);
 uint32_t color_tc_blob_bytes();
 int color_tc_status(uint32_t* out16);
+int launch_dir_bias(const float* viewdirs, const float* wdir, const float* c0, const float* c1, float* out,
+                    uint32_t n_rays, cudaStream_t st);
 void color_tc_pack_chunk(const float* wt_rows, uint8_t* dst);
 int sample_encode_lmax(int L);
 // h1 column c holds hidden unit kH1Perm(c) of density_layer.0 (layout written by sample_encode_kernel)

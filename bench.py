@@ -261,6 +261,11 @@ def main():
             achieved = bytes_total / (fam_ms[dom] * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": f"sample_encode_kernel ({dom})", "achieved": achieved,
                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                        "note": "achieved = ALGORITHMIC gather bytes (768*L B per ray-sample) / time; the gathers are "
+                                "served mostly from L1/L2 (the 101 MB proposal table is L2-resident, neighbouring "
+                                "rays share cells), so measured DRAM `traffic` per launch is far below the algorithmic "
+                                "bytes and frac can exceed 1; the kernel is bound by L1 wavefronts / issue, see "
+                                "profiles/r1_summary.md",
                         "peak_source": how, "launches": fam[dom][1], "avg_launch_ms": fam_ms[dom] / max(fam[dom][1], 1),
                         "algorithmic_bytes_per_launch": bytes_total / max(fam[dom][1], 1)}
         else:

@@ -169,11 +169,9 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// round-to-nearest (ties away) to TF32 = cvt.rna.tf32.f32, done with two integer ops: the conversion pipe issues
+// at a quarter of the ALU rate and 64 conversions per row and chunk made it the producers' bottleneck
+__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
 // write one row (32 fp32 values) of an A chunk as hi / lo TF32 tiles in the SWIZZLE_128B K-major layout
 __device__ __forceinline__ void store_a_row(uint8_t* slot, int row, const float (&v)[32]) {
@@ -258,7 +256,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         // profiling (debug_flags bit 2): thread 0 of each group in CTA 0 -> dbg[16 + 8 g ...]: total, waits on
         // A_EMPTY / ACC3_FULL / ACC4_FULL+PART, time in h1 chunks / dir chunks / tmem chunks (kilo-cycles)
         const bool prof = (p.debug_flags & 4u) != 0 && t == 0 && blockIdx.x == 0;
-        long long pw_aempty = 0, pw_acc3 = 0, pw_epi = 0, pt_h1 = 0, pt_dir = 0, pt_tm = 0;
+        long long pw_aempty = 0, pw_acc3 = 0, pw_epi = 0, pt_h1 = 0, pt_dir = 0, pt_tm = 0, pt_store = 0, pt_fence = 0;
         const long long pt_begin = clock64();
 
         // drain this group's half of acc4 for tile `tl` (iteration `itp`), rgb layer, sigmoid, store
@@ -347,12 +345,14 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                         tc_fence_after();
                     }
                     uint32_t r[32];
+                    const long long tl0 = prof ? clock64() : 0;
                     tmem_ld32_issue(lane_taddr + (uint32_t)(32 * j), r);
                     const float4* b0 = reinterpret_cast<const float4*>(bias0 + 32 * j);
                     float4 bb[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) bb[q] = __ldg(b0 + q);  // overlaps the TMEM load
                     tmem_ld_wait();
+                    if (prof) pt_dir += clock64() - tl0;  // profiler slot "dir" = TMEM load + bias load latency
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         v[4 * q] = fmaxf(__uint_as_float(r[4 * q]) + bb[q].x, 0.f);
@@ -370,8 +370,11 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                 const long long tb2 = prof ? clock64() : 0;
                 if (prof) { pw_aempty += tb2 - tb; tw += tb2 - tb; }
                 if (!(p.debug_flags & 2u)) store_a_row(my_slot, t, v);  // bit 1: profiling experiment, skip A stores
+                const long long ts1 = prof ? clock64() : 0;
                 fence_proxy_async();
+                const long long ts2 = prof ? clock64() : 0;
                 mbar_arrive(BAR(A_FULL0 + g));
+                if (prof) { pt_store += ts1 - tb2; pt_fence += ts2 - ts1; }
                 ++k;
                 if (prof) {
                     const long long work = clock64() - tc0 - tw;
@@ -392,6 +395,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
             uint32_t* d = p.dbg + 16 + 8 * g;
             d[0] = (uint32_t)((clock64() - pt_begin) >> 10); d[1] = (uint32_t)(pw_aempty >> 10); d[2] = (uint32_t)(pw_acc3 >> 10);
             d[3] = (uint32_t)(pw_epi >> 10); d[4] = (uint32_t)(pt_h1 >> 10); d[5] = (uint32_t)(pt_dir >> 10); d[6] = (uint32_t)(pt_tm >> 10);
+            d[7] = (uint32_t)((pt_store >> 10) | ((pt_fence >> 10) << 16));
         }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one thread) ==================================================

@@ -28,30 +28,40 @@ constexpr int kSampleThreads = 128;
 #define UC_MINB_LARGE 4   // LMAX <= 10 -> 128 registers (5 -> 96 registers spills with FFMA2 register pairs; measured slower)
 #endif
 
+// entry address = level base + 16 * index as ONE IMAD.WIDE.U32 (the compiler otherwise re-associates the level offset
+// into a 64-bit add + LEA pair per corner: 4 instructions per address in an instruction-issue-bound kernel)
+__device__ __forceinline__ const float4* entry_ptr(uint64_t tab, uint32_t idx) {
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(idx), "l"(tab));
+    return reinterpret_cast<const float4*>(a);
+}
+
 // MODE: 0 dense (index < table size, no reduction), 1 hashed with power-of-two table, 2 generic (runtime flags)
 template <int MODE>
-__device__ __forceinline__ void gather8(const GridLevel& lv, const float4* __restrict__ tab, const CellCoords& c,
+__device__ __forceinline__ void gather8(const GridLevel& lv, const float4* __restrict__ tab_, const CellCoords& c,
                                         float4 (&v)[8]) {
+    const uint64_t tab = reinterpret_cast<uint64_t>(tab_);
     if constexpr (MODE == 0) {
         const uint32_t b00 = c.ix + c.iy * lv.stride1 + c.iz * lv.stride2;
         const uint32_t b10 = b00 + lv.stride1, b01 = b00 + lv.stride2, b11 = b10 + lv.stride2;
-        v[0] = ldg_f4(tab + b00); v[1] = ldg_f4(tab + b00 + 1);
-        v[2] = ldg_f4(tab + b10); v[3] = ldg_f4(tab + b10 + 1);
-        v[4] = ldg_f4(tab + b01); v[5] = ldg_f4(tab + b01 + 1);
-        v[6] = ldg_f4(tab + b11); v[7] = ldg_f4(tab + b11 + 1);
+        const float4 *p00 = entry_ptr(tab, b00), *p10 = entry_ptr(tab, b10), *p01 = entry_ptr(tab, b01), *p11 = entry_ptr(tab, b11);
+        v[0] = ldg_f4(p00); v[1] = ldg_f4(p00 + 1);
+        v[2] = ldg_f4(p10); v[3] = ldg_f4(p10 + 1);
+        v[4] = ldg_f4(p01); v[5] = ldg_f4(p01 + 1);
+        v[6] = ldg_f4(p11); v[7] = ldg_f4(p11 + 1);
     } else if constexpr (MODE == 1) {
         const uint32_t hy0 = c.iy * 2654435761u, hy1 = hy0 + 2654435761u;
         const uint32_t hz0 = c.iz * 805459861u, hz1 = hz0 + 805459861u;
         const uint32_t a00 = hy0 ^ hz0, a10 = hy1 ^ hz0, a01 = hy0 ^ hz1, a11 = hy1 ^ hz1;
         const uint32_t x0 = c.ix, x1 = c.ix + 1, m = lv.pow2_mask;
-        v[0] = ldg_f4(tab + ((x0 ^ a00) & m)); v[1] = ldg_f4(tab + ((x1 ^ a00) & m));
-        v[2] = ldg_f4(tab + ((x0 ^ a10) & m)); v[3] = ldg_f4(tab + ((x1 ^ a10) & m));
-        v[4] = ldg_f4(tab + ((x0 ^ a01) & m)); v[5] = ldg_f4(tab + ((x1 ^ a01) & m));
-        v[6] = ldg_f4(tab + ((x0 ^ a11) & m)); v[7] = ldg_f4(tab + ((x1 ^ a11) & m));
+        v[0] = ldg_f4(entry_ptr(tab, (x0 ^ a00) & m)); v[1] = ldg_f4(entry_ptr(tab, (x1 ^ a00) & m));
+        v[2] = ldg_f4(entry_ptr(tab, (x0 ^ a10) & m)); v[3] = ldg_f4(entry_ptr(tab, (x1 ^ a10) & m));
+        v[4] = ldg_f4(entry_ptr(tab, (x0 ^ a01) & m)); v[5] = ldg_f4(entry_ptr(tab, (x1 ^ a01) & m));
+        v[6] = ldg_f4(entry_ptr(tab, (x0 ^ a11) & m)); v[7] = ldg_f4(entry_ptr(tab, (x1 ^ a11) & m));
     } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            v[k] = ldg_f4(tab + level_index(lv, c.ix + (k & 1), c.iy + ((k >> 1) & 1), c.iz + ((k >> 2) & 1)));
+            v[k] = ldg_f4(entry_ptr(tab, level_index(lv, c.ix + (k & 1), c.iy + ((k >> 1) & 1), c.iz + ((k >> 2) & 1))));
     }
 }
 

@@ -1,26 +1,34 @@
-// Colour MLP on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate through the 3xTF32 split.
+// Colour MLP on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate through a 3-term FP16 split.
 //
-//   a   = relu(P0 [h1, direnc] + c0')            (K = 96,  N = 256)      -> TMEM accumulator "acc3"
-//   a2  = relu(P1 [h1, direnc] + V1a a + c1')    (K = 352, N = 256)      -> TMEM accumulator "acc4"
-//   rgb = sigmoid(R a2 + r0) * (1 + 2 pad) - pad (N = 3, CUDA cores in the epilogue)
-// (the activation-free bottleneck layer of models.py:L438-441/L601 is folded into P0 / P1 on the host.)
+//   a   = relu(P0 h1 + [P0d direnc + c0'])            (K = 64,  N = 256)      -> TMEM accumulator "acc3"
+//   a2  = relu(P1 h1 + V1a a + [P1d direnc + c1'])    (K = 320, N = 256)      -> TMEM accumulator "acc4"
+//   rgb = sigmoid(R a2 + r0) * (1 + 2 pad) - pad      (N = 3, CUDA cores in the epilogue)
+// (the activation-free bottleneck layer of models.py:L438-441/L601 is folded into P0 / P1 on the host; the bracketed
+//  view-direction terms are per-ray biases from dir_bias_kernel.)
 //
-// Why 3xTF32: the parity bar is rgb L-inf < 1e-4 against an fp32 reference.  One TF32 pass (10-bit mantissa)
-// leaves ~1e-3 on the pre-activations.  Splitting x = hi + lo (both TF32-representable) and accumulating
-// hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator keeps ~2^-21 relative error per product at 3 MMAs per
-// k-step, still ~5x the fp32 CUDA-core rate.
+// Why a split: the parity bar is rgb L-inf < 1e-4 against an fp32 reference and one low-precision pass (TF32/BF16/FP16)
+// leaves ~1e-3 on the pre-activations.  Every operand is written as x * s = hi + lo with hi, lo in FP16 (s a power
+// of two chosen so that hi uses the upper part of the FP16 range: 22 significant bits per operand) and
+// hi*hi + lo*hi + hi*lo is accumulated in the fp32 TMEM accumulator: ~2^-22 relative error per product, the same as
+// the 3xTF32 split this kernel used first, at HALF the tensor-pipe time (kind::f16 retires K = 16 per instruction at
+// the rate kind::tf32 retires K = 8) and half the shared-memory / L2 operand traffic (2-byte elements).
+// Range: activations are scaled by kActScale = 8, so |h1|, |a| must stay below 65504 / 8 = 8188; larger values become
+// inf in the FP16 hi part and surface as NaN colours (never as silently wrong ones) - use color_mlp = 0 for such nets.
 //
 // CTA = one 128-row tile at a time (persistent over tiles), 10 warps:
 //   warps 0-7  two producer / epilogue warpgroups (thread t of a group owns row t; group g fills A slot g, i.e.
-//              the chunks with c % 2 == g).  They build the A operand chunk by chunk in shared memory
-//              in the UMMA canonical K-major SWIZZLE_128B layout (hi tile + lo tile): from global h1 / the
-//              computed view-direction encoding, or from acc3 in TMEM (tcgen05.ld -> +bias -> relu -> split).
-//              Finally drains acc4, applies the rgb layer + sigmoid and writes the sample colours.
-//   warp 8     one elected thread issues tcgen05.mma (M=128, N=256, K=8, kind::tf32) and tcgen05.commit.
+//              the chunks with c % 2 == g).  They build the A operand chunk by chunk (64 K-elements = one 128-byte
+//              swizzle row of FP16) in shared memory in the UMMA canonical K-major SWIZZLE_128B layout (hi tile +
+//              lo tile): from global h1, or from acc3 in TMEM (tcgen05.ld -> scale + bias -> relu -> split).
+//              Finally they drain acc4, apply the rgb layer + sigmoid and write the sample colours.
+//   warp 8     one elected thread issues tcgen05.mma (M=128, N=256, K=16, kind::f16) and tcgen05.commit.
 //   warp 9     one elected thread streams the pre-swizzled weight chunks (hi|lo, 64 KB each) from L2 with
 //              cp.async.bulk (TMA bulk copy, completes on an mbarrier).
 // Pipelines: A ring (2 x 32 KB) and B ring (2 x 64 KB) with full/empty mbarriers; acc3/acc4 full/empty
 // mbarriers order MMA vs. TMEM drains.  TMEM: all 512 columns (acc3 = [0,256), acc4 = [256,512)).
+#include <cuda_fp16.h>
+
+#include <cmath>
 #include <cstring>
 
 #include "ray_march.cuh"
@@ -31,11 +39,12 @@ namespace tc {
 
 constexpr int kTileM = 128;
 constexpr int kN = 256;
-constexpr int kKC = 32;                       // K elements per chunk = one 128-byte swizzle row
-constexpr int kSteps = 12;                    // chunks per tile (see the step table below)
-constexpr uint32_t kATileBytes = kTileM * kKC * 4;   // 16 KB (one of hi / lo)
+constexpr int kKC = 64;                       // K elements per chunk = one 128-byte swizzle row of FP16
+constexpr int kSteps = 6;                     // chunks per tile (see the step table below)
+constexpr float kActScale = 8.f;              // power-of-two scale of the A operand (h1, a) before the FP16 split
+constexpr uint32_t kATileBytes = kTileM * kKC * 2;   // 16 KB (one of hi / lo)
 constexpr uint32_t kASlotBytes = 2 * kATileBytes;    // 32 KB
-constexpr uint32_t kBTileBytes = kN * kKC * 4;       // 32 KB
+constexpr uint32_t kBTileBytes = kN * kKC * 2;       // 32 KB
 constexpr uint32_t kBSlotBytes = 2 * kBTileBytes;    // 64 KB
 constexpr int kStages = 2;
 constexpr uint32_t kSmemA = 0;
@@ -54,9 +63,9 @@ constexpr uint32_t kSmemTotal = kSmemMisc + kMiscBytes + 1024;  // +1024: manual
 constexpr int kThreads = 320;                     // warps 0-3 / 4-7: producer groups, 8: MMA, 9: weight loader
 constexpr int kMmaWarp = 8;
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=F16 (0) [7,10), b=F16 (0) [10,13),
 // a/b K-major, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
 enum Bar { A_FULL0 = 0, A_FULL1, A_EMPTY0, A_EMPTY1, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, ACC3_FULL, ACC4_FULL,
            ACC3_EMPTY, ACC4_EMPTY, PART_FULL, PART_EMPTY, NUM_BARS };
@@ -131,12 +140,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
         : "memory");
 }
@@ -169,22 +178,27 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// round-to-nearest (ties away) to TF32 = cvt.rna.tf32.f32, done with two integer ops: the conversion pipe issues
-// at a quarter of the ALU rate and 64 conversions per row and chunk made it the producers' bottleneck
-__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+// x (already scaled) -> FP16 hi / lo pair for two neighbouring K elements: hi = rn(x), lo = rn(x - hi)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
-// write one row (32 fp32 values) of an A chunk as hi / lo TF32 tiles in the SWIZZLE_128B K-major layout
-__device__ __forceinline__ void store_a_row(uint8_t* slot, int row, const float (&v)[32]) {
+// write half `hf` (32 of the 64 K elements) of one row of an A chunk as hi / lo FP16 tiles in the SWIZZLE_128B
+// K-major layout: row r at (r/8)*1024 + (r%8)*128, 16-byte piece pc (8 elements) at ((pc ^ (r%8)) * 16)
+__device__ __forceinline__ void store_a_half(uint8_t* slot, int row, int hf, const float (&v)[32]) {
     uint8_t* base = slot + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int q = 0; q < 4; ++q) {
         uint4 hi, lo;
-        uint32_t h;
-        h = to_tf32(v[4 * c + 0]); hi.x = h; lo.x = to_tf32(v[4 * c + 0] - __uint_as_float(h));
-        h = to_tf32(v[4 * c + 1]); hi.y = h; lo.y = to_tf32(v[4 * c + 1] - __uint_as_float(h));
-        h = to_tf32(v[4 * c + 2]); hi.z = h; lo.z = to_tf32(v[4 * c + 2] - __uint_as_float(h));
-        h = to_tf32(v[4 * c + 3]); hi.w = h; lo.w = to_tf32(v[4 * c + 3] - __uint_as_float(h));
-        const int pc = (c ^ (row & 7)) * 16;
+        split2(v[8 * q + 0], v[8 * q + 1], hi.x, lo.x);
+        split2(v[8 * q + 2], v[8 * q + 3], hi.y, lo.y);
+        split2(v[8 * q + 4], v[8 * q + 5], hi.z, lo.z);
+        split2(v[8 * q + 6], v[8 * q + 7], hi.w, lo.w);
+        const int pc = ((4 * hf + q) ^ (row & 7)) * 16;
         *reinterpret_cast<uint4*>(base + pc) = hi;
         *reinterpret_cast<uint4*>(base + kATileBytes + pc) = lo;
     }
@@ -195,15 +209,18 @@ __device__ __forceinline__ void store_a_row(uint8_t* slot, int row, const float 
 using namespace tc;
 
 // Step table of one tile (A chunk source x weight chunk = step index in the blob -> accumulator):
-//   0: h1[0:32]  x P0 -> acc3 (init)     2: h1[0:32]  x P1 -> acc4 (init)     4..11: a[32j:32j+32] x V1a -> acc4
-//   1: h1[32:64] x P0 -> acc3, commit    3: h1[32:64] x P1 -> acc4                   11: commit acc4
+//   0: h1[0:64] x P0 -> acc3 (init), commit acc3      2..5: a[64j:64j+64] x V1a -> acc4 (j = step - 2)
+//   1: h1[0:64] x P1 -> acc4 (init)                      5: commit acc4
 // The view-direction encoding is constant per ray, so its contribution (P0d direnc + c0', P1d direnc + c1') is
 // evaluated once per ray by dir_bias_kernel (fp32 FMAs) and added as a per-ray bias when the accumulators are
-// drained: two of fourteen MMA steps and all sinf() evaluations leave this kernel.
+// drained: no MMA step and no sinf() evaluation for it in this kernel.
 // Producer warpgroup g (0/1) builds the chunks with (c & 1) == g into A slot g, so the two groups alternate and
 // each chunk's production overlaps the MMAs of the previous one.  The final epilogue of tile i (drain acc4, rgb
 // layer) is split by accumulator columns between the groups and is executed *after* each group has produced its
 // first chunk of tile i+1, so the tensor pipe already works on the next tile while acc4 is drained.
+// Scales: A operands carry kActScale, the weights of acc3 / acc4 carry the power-of-two factors chosen by the host
+// (color_tc_weight_scale); acc3 * k0 + bias0 (bias0 pre-multiplied by kActScale) is directly the scaled `a`,
+// acc4 * k1 + bias1 the unscaled pre-activation of the last hidden layer.
 __global__ void __launch_bounds__(kThreads, 1)
 color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -256,7 +273,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         // profiling (debug_flags bit 2): thread 0 of each group in CTA 0 -> dbg[16 + 8 g ...]: total, waits on
         // A_EMPTY / ACC3_FULL / ACC4_FULL+PART, time in h1 chunks / dir chunks / tmem chunks (kilo-cycles)
         const bool prof = (p.debug_flags & 4u) != 0 && t == 0 && blockIdx.x == 0;
-        long long pw_aempty = 0, pw_acc3 = 0, pw_epi = 0, pt_h1 = 0, pt_dir = 0, pt_tm = 0, pt_store = 0, pt_fence = 0;
+        long long pw_aempty = 0, pw_acc3 = 0, pw_epi = 0, pt_h1 = 0, pt_tm = 0;
         const long long pt_begin = clock64();
 
         // drain this group's half of acc4 for tile `tl` (iteration `itp`), rgb layer, sigmoid, store
@@ -264,6 +281,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
             if (!mbar_wait(BAR(ACC4_FULL), itp & 1, p.dbg, 3, ACC4_FULL, itp, 99)) return false;
             tc_fence_after();
             float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+            const float k1 = p.k1;
             const uint32_t erow = tl * kTileM + t;
             const float4* bias1 = reinterpret_cast<const float4*>(
                 p.dir_bias + (size_t)((erow < p.n_rows ? erow : 0u) / (uint32_t)p.S) * 512 + 256 + g * 128);
@@ -285,7 +303,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                     const float bq[4] = {bb[q].x, bb[q].y, bb[q].z, bb[q].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float a2 = fmaxf(__uint_as_float(cur[4 * q + e]) + bq[e], 0.f);
+                        const float a2 = fmaxf(fmaf(__uint_as_float(cur[4 * q + e]), k1, bq[e]), 0.f);
                         const float4 w = sR[col + 4 * q + e];
                         o0 = fmaf(a2, w.x, o0);
                         o1 = fmaf(a2, w.y, o1);
@@ -319,66 +337,78 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
             const bool valid = row < p.n_rows;
             const float* h1row = p.h1 + (size_t)(valid ? row : 0) * 64;
             const float* bias0 = p.dir_bias + (size_t)((valid ? row : 0u) / (uint32_t)p.S) * 512;  // per-ray [c0' | c1'] rows
-            float hkeep[32];
 #pragma unroll 1
             for (int c = g; c < kSteps; c += 2) {
-                float v[32];
                 const long long tc0 = prof ? clock64() : 0;
                 long long tw = 0;
-                if (c < 2) {  // this group's half of the h1 row: loaded once, kept in registers for chunk c + 2
-                    const float4* src = reinterpret_cast<const float4*>(h1row + 32 * g);
+                if (c < 2) {
+                    // the h1 row (64 values): group 0 pairs it with P0 (step 0), group 1 with P1 (step 1)
+                    float4 x[16];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float4 x = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        hkeep[4 * q] = x.x; hkeep[4 * q + 1] = x.y; hkeep[4 * q + 2] = x.z; hkeep[4 * q + 3] = x.w;
+                    for (int q = 0; q < 16; ++q)
+                        x[q] = valid ? __ldg(reinterpret_cast<const float4*>(h1row) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const long long tb = prof ? clock64() : 0;
+                    if (!mbar_wait(BAR(A_EMPTY0 + g), (k & 1) ^ 1, p.dbg, 2, A_EMPTY0 + g, it, c)) goto teardown;
+                    if (prof) { tw = clock64() - tb; pw_aempty += tw; }
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float v[32];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            v[4 * q] = x[8 * hf + q].x * kActScale; v[4 * q + 1] = x[8 * hf + q].y * kActScale;
+                            v[4 * q + 2] = x[8 * hf + q].z * kActScale; v[4 * q + 3] = x[8 * hf + q].w * kActScale;
+                        }
+                        store_a_half(my_slot, t, hf, v);
                     }
-                }
-                if (c < 4) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = hkeep[i];
                 } else {
-                    const int j = c - 4;
+                    const int j = c - 2;  // columns [64 j, 64 j + 64) of acc3
                     if (j < 2) {  // first TMEM chunk of this group for this tile
                         const long long ta = prof ? clock64() : 0;
                         if (!mbar_wait(BAR(ACC3_FULL), it & 1, p.dbg, 1, ACC3_FULL, it, c)) goto teardown;
                         if (prof) { tw = clock64() - ta; pw_acc3 += tw; }
                         tc_fence_after();
                     }
-                    uint32_t r[32];
-                    const long long tl0 = prof ? clock64() : 0;
-                    tmem_ld32_issue(lane_taddr + (uint32_t)(32 * j), r);
-                    const float4* b0 = reinterpret_cast<const float4*>(bias0 + 32 * j);
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32_issue(lane_taddr + (uint32_t)(64 * j), r0);
+                    tmem_ld32_issue(lane_taddr + (uint32_t)(64 * j + 32), r1);
+                    const float4* b0 = reinterpret_cast<const float4*>(bias0 + 64 * j);
                     float4 bb[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) bb[q] = __ldg(b0 + q);  // overlaps the TMEM load
+                    for (int q = 0; q < 8; ++q) bb[q] = __ldg(b0 + q);  // overlaps the TMEM loads
                     tmem_ld_wait();
-                    if (prof) pt_dir += clock64() - tl0;  // profiler slot "dir" = TMEM load + bias load latency
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        v[4 * q] = fmaxf(__uint_as_float(r[4 * q]) + bb[q].x, 0.f);
-                        v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + bb[q].y, 0.f);
-                        v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + bb[q].z, 0.f);
-                        v[4 * q + 3] = fmaxf(__uint_as_float(r[4 * q + 3]) + bb[q].w, 0.f);
-                    }
-                    if (j >= 6) {  // this group's part of acc3 is drained
+                    if (j >= 2) {  // this group's part of acc3 is in registers
                         tc_fence_before();
                         mbar_arrive(BAR(ACC3_EMPTY));
                     }
+                    const long long tb = prof ? clock64() : 0;
+                    if (!mbar_wait(BAR(A_EMPTY0 + g), (k & 1) ^ 1, p.dbg, 2, A_EMPTY0 + g, it, c)) goto teardown;
+                    if (prof) { const long long d = clock64() - tb; pw_aempty += d; tw += d; }
+                    const float k0 = p.k0;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float v[32];
+                        if (hf) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) bb[q] = __ldg(b0 + 8 + q);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t* rr = hf ? r1 : r0;
+                            const float4 bq = bb[q];
+                            v[4 * q] = fmaxf(fmaf(__uint_as_float(rr[4 * q]), k0, bq.x), 0.f);
+                            v[4 * q + 1] = fmaxf(fmaf(__uint_as_float(rr[4 * q + 1]), k0, bq.y), 0.f);
+                            v[4 * q + 2] = fmaxf(fmaf(__uint_as_float(rr[4 * q + 2]), k0, bq.z), 0.f);
+                            v[4 * q + 3] = fmaxf(fmaf(__uint_as_float(rr[4 * q + 3]), k0, bq.w), 0.f);
+                        }
+                        store_a_half(my_slot, t, hf, v);
+                    }
                 }
-                const long long tb = prof ? clock64() : 0;
-                if (!mbar_wait(BAR(A_EMPTY0 + g), (k & 1) ^ 1, p.dbg, 2, A_EMPTY0 + g, it, c)) goto teardown;
-                const long long tb2 = prof ? clock64() : 0;
-                if (prof) { pw_aempty += tb2 - tb; tw += tb2 - tb; }
-                if (!(p.debug_flags & 2u)) store_a_row(my_slot, t, v);  // bit 1: profiling experiment, skip A stores
-                const long long ts1 = prof ? clock64() : 0;
                 fence_proxy_async();
-                const long long ts2 = prof ? clock64() : 0;
                 mbar_arrive(BAR(A_FULL0 + g));
-                if (prof) { pt_store += ts1 - tb2; pt_fence += ts2 - ts1; }
                 ++k;
                 if (prof) {
                     const long long work = clock64() - tc0 - tw;
-                    if (c < 4) pt_h1 += work; else pt_tm += work;
+                    if (c < 2) pt_h1 += work; else pt_tm += work;
                 }
                 if (c == g && it > 0) {
                     const long long te = prof ? clock64() : 0;
@@ -394,8 +424,8 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         if (prof) {
             uint32_t* d = p.dbg + 16 + 8 * g;
             d[0] = (uint32_t)((clock64() - pt_begin) >> 10); d[1] = (uint32_t)(pw_aempty >> 10); d[2] = (uint32_t)(pw_acc3 >> 10);
-            d[3] = (uint32_t)(pw_epi >> 10); d[4] = (uint32_t)(pt_h1 >> 10); d[5] = (uint32_t)(pt_dir >> 10); d[6] = (uint32_t)(pt_tm >> 10);
-            d[7] = (uint32_t)((pt_store >> 10) | ((pt_fence >> 10) << 16));
+            d[3] = (uint32_t)(pw_epi >> 10); d[4] = (uint32_t)(pt_h1 >> 10); d[5] = 0; d[6] = (uint32_t)(pt_tm >> 10);
+            d[7] = 0;
         }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one thread) ==================================================
@@ -411,7 +441,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                     long long t0 = prof ? clock64() : 0;
                     if (s == 0 && !mbar_wait(BAR(ACC3_EMPTY), (it & 1) ^ 1, p.dbg, 4, ACC3_EMPTY, it, s)) goto teardown;
                     if (prof) { const long long t1 = clock64(); w_acc3 += t1 - t0; t0 = t1; }
-                    if (s == 2 && !mbar_wait(BAR(ACC4_EMPTY), (it & 1) ^ 1, p.dbg, 5, ACC4_EMPTY, it, s)) goto teardown;
+                    if (s == 1 && !mbar_wait(BAR(ACC4_EMPTY), (it & 1) ^ 1, p.dbg, 5, ACC4_EMPTY, it, s)) goto teardown;
                     if (prof) { const long long t1 = clock64(); w_acc4 += t1 - t0; t0 = t1; }
                     if (!mbar_wait(BAR(B_FULL0 + slot), phase, p.dbg, 6, B_FULL0 + slot, it, s)) goto teardown;
                     if (prof) { const long long t1 = clock64(); w_b += t1 - t0; t0 = t1; }
@@ -422,19 +452,19 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                     const uint32_t a_lo = a_hi + kATileBytes;
                     const uint32_t b_hi = smem_u32(smem + kSmemB + slot * kBSlotBytes);
                     const uint32_t b_lo = b_hi + kBTileBytes;
-                    const uint32_t acc = tmem_base + (s < 2 ? 0u : 256u);
-                    const bool init = (s == 0 || s == 2);
+                    const uint32_t acc = tmem_base + (s == 0 ? 0u : 256u);
+                    const bool init = s < 2;
 #pragma unroll
-                    for (int ks = 0; ks < kKC / 8; ++ks) {
+                    for (int ks = 0; ks < kKC / 16; ++ks) {  // K = 16 per instruction = 32 bytes of the swizzled row
                         const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
                         const uint64_t dbh = make_desc(b_hi + ks * 32), dbl = make_desc(b_lo + ks * 32);
-                        umma_tf32(acc, dah, dbh, (init && ks == 0) ? 0u : 1u);
-                        umma_tf32(acc, dal, dbh, 1u);
-                        umma_tf32(acc, dah, dbl, 1u);
+                        umma_f16(acc, dah, dbh, (init && ks == 0) ? 0u : 1u);
+                        umma_f16(acc, dal, dbh, 1u);
+                        umma_f16(acc, dah, dbl, 1u);
                     }
                     umma_commit(BAR(A_EMPTY0 + slot));
                     umma_commit(BAR(B_EMPTY0 + slot));
-                    if (s == 1) umma_commit(BAR(ACC3_FULL));
+                    if (s == 0) umma_commit(BAR(ACC3_FULL));
                     if (s == kSteps - 1) umma_commit(BAR(ACC4_FULL));
                     slot ^= 1;
                     phase ^= (slot == 0);
@@ -477,8 +507,9 @@ teardown:
     }
 }
 
-// Per-ray constant part of both colour layers: out[ray][0:256] = c0' + P0d direnc(viewdir), out[ray][256:512] =
-// c1' + P1d direnc(viewdir), direnc = pos_enc(viewdirs, 0, 4) (coord.py:L214-225, 27 values).  fp32 FMAs.
+// Per-ray constant part of both colour layers: out[ray][0:256] = kActScale * (c0' + P0d direnc(viewdir)) (the scale of
+// the FP16 A operand, see color_mlp_tc_kernel), out[ray][256:512] = c1' + P1d direnc(viewdir),
+// direnc = pos_enc(viewdirs, 0, 4) (coord.py:L214-225, 27 values).  fp32 FMAs.
 __global__ void __launch_bounds__(256)
 dir_bias_kernel(const float* __restrict__ viewdirs, const float* __restrict__ wdir /* [2][32][256] */,
                 const float* __restrict__ c0, const float* __restrict__ c1, float* __restrict__ out, uint32_t n_rays) {
@@ -516,7 +547,7 @@ dir_bias_kernel(const float* __restrict__ viewdirs, const float* __restrict__ wd
             a0 = fmaf(w0[k], enc[r][k], a0);
             a1 = fmaf(w1[k], enc[r][k], a1);
         }
-        out[(size_t)(ray0 + r) * 512 + n] = a0;
+        out[(size_t)(ray0 + r) * 512 + n] = a0 * kActScale;  // exact (power of two)
         out[(size_t)(ray0 + r) * 512 + 256 + n] = a1;
     }
 }
@@ -560,28 +591,31 @@ int launch_color_mlp_tc(const ColorTcParams& p_in, cudaStream_t st) {
 }
 
 uint32_t color_tc_blob_bytes() { return kSteps * kBSlotBytes; }
+float color_tc_act_scale() { return kActScale; }
 
-// Host: lay the folded weights out as the kernel consumes them.  Wt chunks are K-major [k][256] fp32 arrays of 32
-// rows each (step order of the kernel); every chunk becomes hi tile | lo tile, each in the UMMA K-major
-// SWIZZLE_128B image: element (n, k) at (n/8)*1024 + (n%8)*128 + ((k/4) ^ (n%8))*16 + (k%4)*4.
-static inline uint32_t tf32_rna_bits(float x) {
-    uint32_t b;
-    memcpy(&b, &x, 4);
-    if ((b & 0x7F800000u) == 0x7F800000u) return b;
-    b += 0x1000u;
-    return b & 0xFFFFE000u;
+// Power-of-two factor that moves the largest |w| of a weight block into [2^13, 2^14): FP16 hi then carries 11
+// significant bits and lo (|lo| <= 2^-11 |w s|) stays a normal FP16 number down to 2^-24 of the largest weight.
+float color_tc_weight_scale(const float* w, size_t n) {
+    float mx = 0.f;
+    for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
+    if (!(mx > 0.f) || !std::isfinite(mx)) return 1.f;
+    int e;
+    frexpf(mx, &e);          // mx = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.f, 14 - e);
 }
-void color_tc_pack_chunk(const float* wt_rows /* [32][256] */, uint8_t* dst /* 64 KB */) {
+
+// Host: lay the folded weights out as the kernel consumes them.  Wt chunks are K-major [k][256] fp32 arrays of 64
+// rows each (step order of the kernel); every chunk becomes hi tile | lo tile of (w * scale), each in the UMMA
+// K-major SWIZZLE_128B image: element (n, k) at (n/8)*1024 + (n%8)*128 + ((k/8) ^ (n%8))*16 + (k%8)*2.
+void color_tc_pack_chunk(const float* wt_rows /* [64][256] */, float scale, uint8_t* dst /* 64 KB */) {
     for (int n = 0; n < kN; ++n)
         for (int k = 0; k < kKC; ++k) {
-            const float w = wt_rows[(size_t)k * kN + n];
-            const uint32_t hb = tf32_rna_bits(w);
-            float hf;
-            memcpy(&hf, &hb, 4);
-            const uint32_t lb = tf32_rna_bits(w - hf);
-            const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((k >> 2) ^ (n & 7)) * 16) + (k & 3) * 4;
-            memcpy(dst + off, &hb, 4);
-            memcpy(dst + kBTileBytes + off, &lb, 4);
+            const float w = wt_rows[(size_t)k * kN + n] * scale;
+            const __half h = __float2half_rn(w);
+            const __half l = __float2half_rn(w - __half2float(h));
+            const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((k >> 3) ^ (n & 7)) * 16) + (k & 7) * 2;
+            memcpy(dst + off, &h, 2);
+            memcpy(dst + kBTileBytes + off, &l, 2);
         }
 }
 

@@ -71,12 +71,13 @@ struct ucnerf_model {
     int np = 0;  // padded colour-MLP width
     DevBuf w2t, b2, v0t, c0, v1t, c1, rt, r0, wblob, wdir, dir_bias;
     uint32_t tc_debug = 0;
+    float tc_k0 = 1.f, tc_k1 = 1.f;   // accumulator scales of the FP16-split tensor-core colour MLP
     bool tc_ok = false;   // tensor-core colour MLP available for these shapes (W = 256, deg_view = 4)
     DevBuf density, h1, rgb_s;
     // host-entry staging
     DevBuf stage_in, stage_out;
     int64_t chunk_rays = 131072;
-    int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 3xTF32 (error if shapes unsupported), 2 = auto
+    int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 FP16 split (error if shapes unsupported), 2 = auto
     bool timing = false;
     float ms[5] = {0, 0, 0, 0, 0};
     uint32_t nlaunch[5] = {0, 0, 0, 0, 0};
@@ -221,12 +222,17 @@ static int build_color(ucnerf_model* m) {
     if (int e = upload(m->v0t, p0t)) return e;
     m->tc_ok = (NP == 256 && d.deg_view == 4);
     if (m->tc_ok) {
-        // step order of color_mlp_tc_kernel: P0 rows [h1 0:32, h1 32:64, dir], P1 rows [h1 0:32, h1 32:64, dir], V1a x8
+        // step order of color_mlp_tc_kernel: P0 (h1 rows) -> acc3; P1 (h1 rows), V1a x4 -> acc4.  Both operand blocks
+        // of one accumulator share one power-of-two weight scale; activations carry color_tc_act_scale().
         std::vector<uint8_t> blob(color_tc_blob_bytes());
-        const size_t cb = blob.size() / 12;
-        for (int s = 0; s < 2; ++s) color_tc_pack_chunk(&p0t[(size_t)(32 * s) * NP], blob.data() + cb * s);
-        for (int s = 0; s < 2; ++s) color_tc_pack_chunk(&v1t[(size_t)(NP + 32 * s) * NP], blob.data() + cb * (2 + s));
-        for (int j = 0; j < 8; ++j) color_tc_pack_chunk(&v1t[(size_t)(32 * j) * NP], blob.data() + cb * (4 + j));
+        const size_t cb = blob.size() / 6;
+        const float sw0 = color_tc_weight_scale(&p0t[0], (size_t)64 * NP);
+        const float sw1 = color_tc_weight_scale(&v1t[0], (size_t)(NP + 64) * NP);  // rows [a (NP) | h1 (64)]
+        color_tc_pack_chunk(&p0t[0], sw0, blob.data());
+        color_tc_pack_chunk(&v1t[(size_t)NP * NP], sw1, blob.data() + cb);
+        for (int j = 0; j < 4; ++j) color_tc_pack_chunk(&v1t[(size_t)(64 * j) * NP], sw1, blob.data() + cb * (2 + j));
+        m->tc_k0 = 1.f / sw0;
+        m->tc_k1 = 1.f / (color_tc_act_scale() * sw1);
         // view-direction rows of both layers for dir_bias_kernel: [2][32][256]
         std::vector<float> wd((size_t)2 * 32 * 256, 0.f);
         for (int k = 0; k < 32; ++k)
@@ -393,6 +399,7 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
                 if (int e = launch_dir_bias(rp.viewdirs, m->wdir.as<float>(), cp.c0, cp.c1, m->dir_bias.as<float>(), n, st)) return e;
                 tp.wblob = m->wblob.as<uint8_t>(); tp.dir_bias = m->dir_bias.as<float>(); tp.rt = cp.rt; tp.r0 = cp.r0;
                 tp.rgb_scale = cp.rgb_scale; tp.rgb_padding = cp.rgb_padding; tp.rgb = cp.rgb; tp.debug_flags = m->tc_debug;
+                tp.k0 = m->tc_k0; tp.k1 = m->tc_k1;
                 if (int e = launch_color_mlp_tc(tp, st)) return e;
             } else {
                 if (int e = launch_color_mlp_simt(cp, m->np, st)) return e;

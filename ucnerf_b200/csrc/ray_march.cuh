@@ -57,14 +57,15 @@ struct ColorParams {
     float* rgb;              // [rows, 3]
 };
 
-// tensor-core variant (color_mlp_tc.cu): W = 256, deg_view = 4 only; weights pre-split / pre-swizzled (wblob)
+// tensor-core variant (color_mlp_tc.cu): W = 256, deg_view = 4 only; weights pre-scaled / pre-split / pre-swizzled (wblob)
 struct ColorTcParams {
     uint32_t n_rows;
     int S;
     const float* h1;         // [rows, 64]
     const float* viewdirs;   // [N, 3]
-    const uint8_t* wblob;    // 12 chunks x (hi tile | lo tile) in UMMA K-major SWIZZLE_128B layout
-    const float* dir_bias;   // [N rays][512]: per-ray biases of both layers (dir_bias_kernel)
+    const uint8_t* wblob;    // 6 chunks x (hi tile | lo tile) FP16 in UMMA K-major SWIZZLE_128B layout
+    const float* dir_bias;   // [N rays][512]: per-ray biases of both layers (dir_bias_kernel; first half x act scale)
+    float k0, k1;            // accumulator -> value factors: 1 / scale(P0), 1 / (act scale * scale(P1, V1a))
     const float *rt, *r0;    // [256][4], [4]
     float rgb_scale, rgb_padding;
     float* rgb;              // [rows, 3]
@@ -96,7 +97,9 @@ uint32_t color_tc_blob_bytes();
 int color_tc_status(uint32_t* out16);
 int launch_dir_bias(const float* viewdirs, const float* wdir, const float* c0, const float* c1, float* out,
                     uint32_t n_rays, cudaStream_t st);
-void color_tc_pack_chunk(const float* wt_rows, uint8_t* dst);
+void color_tc_pack_chunk(const float* wt_rows, float scale, uint8_t* dst);
+float color_tc_weight_scale(const float* w, size_t n);
+float color_tc_act_scale();
 int sample_encode_lmax(int L);
 // h1 column c holds hidden unit kH1Perm(c) of density_layer.0 (layout written by sample_encode_kernel)
 inline int h1_perm(int c) { return (c / 16) + 4 * (c % 16); }  // padded level count used by the kernel instantiation (0 = unsupported)

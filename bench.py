@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--chunk-rays", type=int, default=0)
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--encode-runs", type=int, default=-1, help="A/B: cell-run reuse in the encode kernel (bit0 prop, bit1 NeRF); -1 = library default")
     ap.add_argument("--tc-debug", type=int, default=0, help="profiling experiment flags for the TC kernel (invalid results)")
     return ap.parse_args()
 
@@ -171,6 +172,8 @@ def main():
         r.set_option("chunk_rays", args.chunk_rays)
     if args.tc_debug:
         r.set_option("tc_debug", args.tc_debug)
+    if args.encode_runs >= 0:
+        r.set_option("encode_runs", args.encode_runs)
     rays_h = synthetic.pinhole_rays(wl.height, wl.width, seed=rank)   # every rank renders its own camera
     n = rays_h["origins"].shape[0]
     rays_d = {k: v.to(dev) for k, v in rays_h.items()}
@@ -235,6 +238,19 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
+    # ---- end-to-end from camera parameters: rays generated on the GPU (ucnerf_render_camera_host) -----------
+    cam = synthetic.pinhole_camera(wl.height, wl.width, seed=rank)
+    for _ in range(max(1, min(args.warmup, 2))):
+        r.render_camera(*cam, want=("packed",), host_out=out_h)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r.render_camera(*cam, want=("packed",), host_out=out_h)
+    ms_cam = (time.perf_counter() - t0) * 1e3     # the call synchronises: wall clock == device + copy time
+    t = torch.tensor([ms_cam], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_cam = float(t.item())
     clocks = sampler.stop() if sampler else None
     checksum = float(out_h["packed"][:, :3].double().mean())
 
@@ -291,6 +307,10 @@ def main():
             "e2e": {"value": total_samples / (ms_e2e * 1e-3), "unit": "ray-samples/s",
                     "h2d_bytes_per_step": int(n * 18 * 4), "d2h_bytes_per_step": int(n * PACKED_WIDTH * 4),
                     "ms_per_step": ms_e2e / args.steps, "api": "ucnerf_render_rays_host (C ABI, pinned host buffers)"},
+            "e2e_camera": {"value": total_samples / (ms_cam * 1e-3), "unit": "ray-samples/s", "h2d_bytes_per_step": 200,
+                           "d2h_bytes_per_step": int(n * PACKED_WIDTH * 4), "ms_per_step": ms_cam / args.steps,
+                           "api": "ucnerf_render_camera_host (rays generated on the GPU from pose + intrinsics; "
+                                  "replaces the loader's numpy pixels_to_rays)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "kernel_time_shares": shares,

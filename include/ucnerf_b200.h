@@ -16,6 +16,11 @@
  *                                   stepfun.py resampling, render.py cast_rays / compute_alpha_weights /
  *                                   volumetric_rendering, MLP.forward models.py:L514-685), called per chunk
  *                                   from render_image models.py:L907-1007.
+ *   ucnerf_generate_rays / ucnerf_render_camera[_host]
+ *                                <- camera_utils.pixels_to_rays internal/camera_utils.py:L448-557 (perspective, no
+ *                                   distortion / NDC), cast_pinhole_rays L611-632 and Dataset._make_ray_batch
+ *                                   internal/datasets.py:L386-476 (near / far broadcast, cam_dirs, float32 cast): the
+ *                                   numpy ray generation of the eval loader, SURVEY.md section 8f N3.
  * The Python-side binding a reference maintainer would add is shown in INTEGRATION.md.
  */
 #ifndef UCNERF_B200_H
@@ -156,6 +161,45 @@ int ucnerf_render_rays(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays* rays
  * non-NULL output back and synchronises the stream.  This is the end-to-end entry bench.py times. */
 int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays* rays_host, double train_frac,
                             const ucnerf_outputs* out_host, void* stream);
+
+/* ---- camera -> rays on the GPU (eval loader's numpy ray generation, camera_utils.py:L448-557) ----
+ * One pinhole camera (perspective, no lens distortion, no NDC).  Matrices are doubles holding the values the
+ * reference holds (its Waymo loader keeps float32 intrinsics / poses; numpy promotes to float64 for the arithmetic,
+ * the results are cast to float32 - the kernel does the same). */
+typedef struct ucnerf_camera {
+    double pixtocam[9];     /* inverse intrinsic matrix, row-major 3x3 (Dataset.pixtocams[i])       */
+    double camtoworld[12];  /* pose, row-major 3x4, OpenGL convention (Dataset.camtoworlds[i])      */
+    uint32_t width, height;
+    float near, far;        /* Dataset.near / .far, broadcast to every ray                          */
+    uint64_t rand_seed;     /* seed of the counter-based N(0,1) cone-basis vectors (render.py:L140) */
+} ucnerf_camera;
+
+/* Writable ray batch for rows [row0, row0 + n_rows) of the image, n = n_rows * width rays in row-major pixel
+ * order (pixel_coordinates, camera_utils.py:L368-370).  Any of origins, cam_dirs, near, far, imageplane [n,2],
+ * rand_vec may be NULL.  rand_vec: the reference draws torch.randn_like(cam_dirs) at every call; here a
+ * reproducible counter-based draw keyed by (rand_seed, pixel index). */
+typedef struct ucnerf_ray_buffers {
+    float* origins;
+    float* directions;
+    float* viewdirs;
+    float* cam_dirs;
+    float* radii;
+    float* near;
+    float* far;
+    float* rand_vec;
+    float* imageplane;
+} ucnerf_ray_buffers;
+
+int ucnerf_generate_rays(const ucnerf_camera* cam, uint32_t row0, uint32_t n_rows, const ucnerf_ray_buffers* out,
+                         void* stream);
+
+/* generate_rays + render_rays for image rows [row0, row0 + n_rows): the frame is rendered from the ~200 bytes of
+ * camera parameters; the ray batch lives in library-owned device memory.  Outputs as in ucnerf_render_rays
+ * (device pointers) / ucnerf_render_rays_host (host pointers, copies back and synchronises). */
+int ucnerf_render_camera(ucnerf_model* m, const ucnerf_camera* cam, uint32_t row0, uint32_t n_rows, double train_frac,
+                         const ucnerf_outputs* out, void* stream);
+int ucnerf_render_camera_host(ucnerf_model* m, const ucnerf_camera* cam, uint32_t row0, uint32_t n_rows,
+                              double train_frac, const ucnerf_outputs* out_host, void* stream);
 
 /* Number of kernels launched by this library in this process so far (bench.py's gpu_launches). */
 uint64_t ucnerf_launch_count(void);

@@ -67,6 +67,30 @@ void h_cone_points(int n_rays, int S, const float* origins, const float* directi
     }
 }
 
+// camera -> rays for rows [row0, row0 + n_rows): out_dir / out_view [n,3], out_plane [n,2], out_radius [n]; normals [n,4]
+void h_pixel_rays(const double* pixtocam, const double* camtoworld, int width, int height, int row0, int n_rows,
+                  uint64_t seed, float* out_dir, float* out_view, float* out_plane, float* out_radius, float* normals) {
+    CameraConst c;
+    for (int i = 0; i < 9; ++i) c.pixtocam[i] = pixtocam[i];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c.rot[3 * i + j] = camtoworld[4 * i + j];
+    c.width = (uint32_t)width; c.height = (uint32_t)height; c.rand_seed = seed;
+    size_t i = 0;
+    for (int y = row0; y < row0 + n_rows; ++y)
+        for (int x = 0; x < width; ++x, ++i) {
+            PixelRay pr;
+            pixel_to_ray(c, x, y, pr);
+            for (int k = 0; k < 3; ++k) { out_dir[3 * i + k] = pr.dir[k]; out_view[3 * i + k] = pr.view[k]; }
+            out_plane[2 * i] = pr.plane[0]; out_plane[2 * i + 1] = pr.plane[1];
+            out_radius[i] = pr.radius;
+            if (normals) {
+                float n4[4];
+                normal4(seed, (uint64_t)y * width + x, n4);
+                for (int k = 0; k < 4; ++k) normals[4 * i + k] = n4[k];
+            }
+        }
+}
+
 // fused-path hash lookup for B points: lv = L x {offset, hashmap_size, stride1, hashed, pow2_mask, scale_bits}
 void h_grid_features(int B, int L, const uint32_t* lvdesc, const float* table, const float* g, float* out) {
     for (int b = 0; b < B; ++b) {

@@ -122,6 +122,22 @@ def test_chunking_and_permutation_invariance():
         assert np.array_equal(c[k], a[k][perm.numpy()]), k
 
 
+@pytest.mark.parametrize("name", ["waymo", "three_level", "config1"])
+def test_encode_cell_run_reuse_is_bit_identical(name):
+    """sample_encode_kernel with cell-run reuse (corners re-gathered only when a multisample point enters a new cell)
+    must give exactly the per-point-gather results: same interpolation and summation order, fewer loads."""
+    cfg, params, _, r = case(name)
+    batch = cases.make_case(name)[2] if name != "waymo" else O.synthetic_rays(4099, seed=5)
+    outs = {}
+    for mode in (0, 1, 2, 3):
+        r.set_option("encode_runs", mode)
+        outs[mode] = run(r, batch)
+    r.set_option("encode_runs", 3)
+    for mode in (1, 2, 3):
+        for k in ("sample_density", "sample_rgb", "rgb", "acc", "depth_raw", "weights_0", f"sdist_{r.num_levels - 1}"):
+            assert np.array_equal(outs[0][k], outs[mode][k]), (mode, k)
+
+
 def test_full_size_properties():
     """65,536 rays with waymo.gin shapes (10.5 M ray-samples): invariants the domain offers."""
     cfg, params, _, r = case("waymo")

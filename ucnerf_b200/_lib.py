@@ -75,12 +75,22 @@ class Outputs(C.Structure):
     ]
 
 
+class Camera(C.Structure):
+    _fields_ = [("pixtocam", C.c_double * 9), ("camtoworld", C.c_double * 12), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("near", C.c_float), ("far", C.c_float), ("rand_seed", C.c_uint64)]
+
+
+class RayBuffers(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in
+                ("origins", "directions", "viewdirs", "cam_dirs", "radii", "near", "far", "rand_vec", "imageplane")]
+
+
 # every symbol include/ucnerf_b200.h declares (tests/test_abi_symbols.py checks the .so exports them)
 EXPORTS = [
     "ucnerf_abi_version", "ucnerf_last_error", "ucnerf_grid_encode_forward", "ucnerf_grid_encode_backward",
     "ucnerf_grad_total_variation", "ucnerf_model_create", "ucnerf_model_refresh", "ucnerf_model_destroy",
     "ucnerf_render_rays", "ucnerf_render_rays_host", "ucnerf_launch_count", "ucnerf_set_option",
-    "ucnerf_get_timing",
+    "ucnerf_get_timing", "ucnerf_generate_rays", "ucnerf_render_camera", "ucnerf_render_camera_host",
 ]
 
 _lib = None
@@ -115,6 +125,9 @@ def load():
     lib.ucnerf_model_destroy.argtypes = [vp]
     lib.ucnerf_render_rays.argtypes = [vp, C.c_uint64, C.POINTER(Rays), C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_render_rays_host.argtypes = [vp, C.c_uint64, C.POINTER(Rays), C.c_double, C.POINTER(Outputs), vp]
+    lib.ucnerf_generate_rays.argtypes = [C.POINTER(Camera), u32, u32, C.POINTER(RayBuffers), vp]
+    lib.ucnerf_render_camera.argtypes = [vp, C.POINTER(Camera), u32, u32, C.c_double, C.POINTER(Outputs), vp]
+    lib.ucnerf_render_camera_host.argtypes = [vp, C.POINTER(Camera), u32, u32, C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.ucnerf_get_timing.argtypes = [vp, c_float_p, C.POINTER(C.c_uint32), C.c_int]
     lib.ucnerf_debug_u_grid.argtypes = [C.c_int, vp]

@@ -347,6 +347,16 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
                         x[q] = valid ? __ldg(reinterpret_cast<const float4*>(h1row) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    // h1 streams from HBM (1 GB per chunk of rays, written by the encode kernel): pull this CTA's NEXT
+                    // tile into L2 now, one whole tile time ahead, so the loads above see L2 instead of DRAM latency
+                    if (g == 0 && !(p.debug_flags & 8u)) {
+                        const uint32_t nrow = (tile + gridDim.x) * kTileM + t;
+                        if (nrow < p.n_rows) {
+                            const float* nx = p.h1 + (size_t)nrow * 64;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
+                        }
+                    }
                     const long long tb = prof ? clock64() : 0;
                     if (!mbar_wait(BAR(A_EMPTY0 + g), (k & 1) ^ 1, p.dbg, 2, A_EMPTY0 + g, it, c)) goto teardown;
                     if (prof) { tw = clock64() - tb; pw_aempty += tw; }

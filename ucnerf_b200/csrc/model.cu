@@ -75,9 +75,11 @@ struct ucnerf_model {
     bool tc_ok = false;   // tensor-core colour MLP available for these shapes (W = 256, deg_view = 4)
     DevBuf density, h1, rgb_s;
     // host-entry staging
-    DevBuf stage_in, stage_out;
+    DevBuf stage_in, stage_out, cam_rays;
     int64_t chunk_rays = 131072;
     int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 FP16 split (error if shapes unsupported), 2 = auto
+    int encode_runs = 0;  // cell-run reuse in sample_encode_kernel (bit 0 = proposal levels, bit 1 = NeRF level): measured
+                          // slower on B200 (profiles/r1_summary.md), kept as an option
     bool timing = false;
     float ms[5] = {0, 0, 0, 0, 0};
     uint32_t nlaunch[5] = {0, 0, 0, 0, 0};
@@ -369,6 +371,7 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         sp.w1p = ls.w1p.as<float>(); sp.b1 = ls.b1.as<float>(); sp.w2 = ls.w2.as<float>(); sp.b2 = ls.b2;
         sp.density = (nerf && o.sample_density) ? o.sample_density + ray0 * S : m->density.as<float>();
         std::memcpy(sp.g2, ls.g2, sizeof(sp.g2));
+        sp.cell_runs = (m->encode_runs >> (nerf ? 1 : 0)) & 1;
         float* rgb_s = nullptr;
         if (nerf) {
             if (int e = m->h1.ensure((size_t)n * S * 64 * sizeof(float))) return e;
@@ -467,7 +470,7 @@ extern "C" int ucnerf_model_destroy(ucnerf_model* m) {
     if (!m) return 0;
     for (auto& ls : m->lv) { ls.w1p.release(); ls.b1.release(); ls.w2.release(); ls.u.release(); ls.sdist.release(); ls.weights.release(); }
     for (DevBuf* b : {&m->w2t, &m->b2, &m->v0t, &m->c0, &m->v1t, &m->c1, &m->rt, &m->r0, &m->density, &m->h1, &m->rgb_s,
-                      &m->stage_in, &m->stage_out, &m->wblob, &m->wdir, &m->dir_bias})
+                      &m->stage_in, &m->stage_out, &m->cam_rays, &m->wblob, &m->wdir, &m->dir_bias})
         b->release();
     resolve_timing(m);
     for (auto& e : m->pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -480,6 +483,7 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
     const std::string k(key);
     if (k == "chunk_rays") { UC_REQUIRE(value >= 1, "chunk_rays must be >= 1"); m->chunk_rays = value; }
     else if (k == "color_mlp") { UC_REQUIRE(value >= 0 && value <= 2, "color_mlp: 0 = fp32 SIMT, 1 = tensor core, 2 = auto"); m->color_mode = (int)value; }
+    else if (k == "encode_runs") { UC_REQUIRE(value >= 0 && value <= 3, "encode_runs: bit 0 = proposal levels, bit 1 = NeRF level"); m->encode_runs = (int)value; }
     else if (k == "timing") m->timing = value != 0;
     else if (k == "tc_debug") m->tc_debug = (uint32_t)value;  // profiling experiments (results invalid when != 0)
     else { set_error("set_option: unknown key " + k); return 1; }
@@ -514,6 +518,119 @@ extern "C" int ucnerf_render_rays(ucnerf_model* m, uint64_t n_rays, const ucnerf
     return 0;
 }
 
+namespace ucnerf {
+
+// Device staging of the outputs a host caller asked for: fills `od` with device pointers into m->stage_out and
+// returns the (host, device, floats) slots to copy back after the render.
+struct OutSlot { float* host; size_t floats; float** dev_field; };
+static int stage_outputs(ucnerf_model* m, size_t N, const ucnerf_outputs* oh, ucnerf_outputs& od, std::vector<OutSlot>& slots) {
+    const int nl = m->num_levels;
+    auto add = [&](float* host, size_t per_ray, float** field) { if (host) slots.push_back({host, N * per_ray, field}); };
+    add(oh->rgb, 3, &od.rgb); add(oh->depth, 1, &od.depth); add(oh->depth_raw, 1, &od.depth_raw); add(oh->acc, 1, &od.acc);
+    add(oh->distance_mean, 1, &od.distance_mean); add(oh->distance_median, 1, &od.distance_median);
+    add(oh->distance_percentile_5, 1, &od.distance_percentile_5); add(oh->distance_percentile_95, 1, &od.distance_percentile_95);
+    for (int l = 0; l < nl; ++l) {
+        add(oh->sdist[l], (size_t)m->lv[l].S + 1, &od.sdist[l]);
+        add(oh->weights[l], (size_t)m->lv[l].S, &od.weights[l]);
+    }
+    add(oh->sample_rgb, (size_t)m->lv[nl - 1].S * 3, &od.sample_rgb);
+    add(oh->sample_density, (size_t)m->lv[nl - 1].S, &od.sample_density);
+    add(oh->packed, 12, &od.packed);
+    size_t tot = 0;
+    for (auto& s : slots) tot += (s.floats + 3) & ~size_t(3);
+    if (int e = m->stage_out.ensure(std::max<size_t>(tot, 4) * sizeof(float))) return e;
+    size_t o2 = 0;
+    for (auto& s : slots) { *s.dev_field = m->stage_out.as<float>() + o2; o2 += (s.floats + 3) & ~size_t(3); }
+    return 0;
+}
+
+static int copy_back_and_check(ucnerf_model* m, std::vector<OutSlot>& slots, cudaStream_t st) {
+    (void)m;
+    for (auto& s : slots)
+        UC_CUDA_OK(cudaMemcpyAsync(s.host, *s.dev_field, s.floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    UC_CUDA_OK(cudaStreamSynchronize(st));
+    uint32_t wd[32];
+    if (int e = color_tc_status(wd)) return e;
+    if (wd[0] != 0) {
+        set_error("color_mlp_tc: pipeline watchdog fired (tag " + std::to_string(wd[0]) + ", barrier " +
+                  std::to_string(wd[3]) + ", step " + std::to_string(wd[6]) + ")");
+        return 5;
+    }
+    return 0;
+}
+
+static int camera_const(const ucnerf_camera* cam, CameraConst& c) {
+    UC_REQUIRE(cam->width >= 1 && cam->height >= 1, "camera: empty image");
+    for (int i = 0; i < 9; ++i) c.pixtocam[i] = cam->pixtocam[i];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) c.rot[3 * i + j] = cam->camtoworld[4 * i + j];
+        c.origin[i] = (float)cam->camtoworld[4 * i + 3];
+        c.cam_dir[i] = (float)(-cam->camtoworld[4 * i + 2]);   // datasets.py:L446
+    }
+    c.near = cam->near; c.far = cam->far; c.width = cam->width; c.height = cam->height; c.rand_seed = cam->rand_seed;
+    return 0;
+}
+
+// rays of image rows [row0, row0 + n_rows) into the model-owned buffer; rd receives the device pointers
+static int camera_rays(ucnerf_model* m, const ucnerf_camera* cam, uint32_t row0, uint32_t n_rows, ucnerf_rays& rd, cudaStream_t st) {
+    UC_REQUIRE((uint64_t)row0 + n_rows <= cam->height, "camera: row range outside the image");
+    const size_t N = (size_t)n_rows * cam->width;
+    if (int e = m->cam_rays.ensure(N * 18 * sizeof(float))) return e;
+    float* b = m->cam_rays.as<float>();
+    RayOutPtrs o{};
+    o.origins = b; o.directions = b + 3 * N; o.viewdirs = b + 6 * N; o.cam_dirs = b + 9 * N; o.rand_vec = b + 12 * N;
+    o.radii = b + 15 * N; o.near = b + 16 * N; o.far = b + 17 * N; o.imageplane = nullptr;
+    CameraConst c;
+    if (int e = camera_const(cam, c)) return e;
+    if (int e = launch_generate_rays(c, row0, n_rows, o, st)) return e;
+    rd.origins = o.origins; rd.directions = o.directions; rd.viewdirs = o.viewdirs; rd.cam_dirs = o.cam_dirs;
+    rd.rand_vec = o.rand_vec; rd.radii = o.radii; rd.near = o.near; rd.far = o.far;
+    return 0;
+}
+
+}  // namespace ucnerf
+
+extern "C" int ucnerf_generate_rays(const ucnerf_camera* cam, uint32_t row0, uint32_t n_rows, const ucnerf_ray_buffers* out,
+                                    void* stream) {
+    UC_REQUIRE(cam && out, "generate_rays: null argument");
+    UC_REQUIRE(out->directions && out->viewdirs && out->radii, "generate_rays: directions, viewdirs and radii are required");
+    UC_REQUIRE((uint64_t)row0 + n_rows <= cam->height, "generate_rays: row range outside the image");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("ucnerf_b200 requires a CUDA device (sm_100a); none is visible - there is no CPU fallback");
+        return 4;
+    }
+    CameraConst c;
+    if (int e = camera_const(cam, c)) return e;
+    RayOutPtrs o{out->origins, out->directions, out->viewdirs, out->cam_dirs, out->radii, out->near, out->far,
+                 out->imageplane, out->rand_vec};
+    return launch_generate_rays(c, row0, n_rows, o, (cudaStream_t)stream);
+}
+
+extern "C" int ucnerf_render_camera(ucnerf_model* m, const ucnerf_camera* cam, uint32_t row0, uint32_t n_rows,
+                                    double train_frac, const ucnerf_outputs* out, void* stream) {
+    UC_REQUIRE(m && cam && out, "render_camera: null argument");
+    if (n_rows == 0) return 0;
+    ucnerf_rays rd{};
+    {
+        std::lock_guard<std::mutex> lk(m->mu);
+        if (int e = camera_rays(m, cam, row0, n_rows, rd, (cudaStream_t)stream)) return e;
+    }
+    return ucnerf_render_rays(m, (uint64_t)n_rows * cam->width, &rd, train_frac, out, stream);
+}
+
+extern "C" int ucnerf_render_camera_host(ucnerf_model* m, const ucnerf_camera* cam, uint32_t row0, uint32_t n_rows,
+                                         double train_frac, const ucnerf_outputs* oh, void* stream) {
+    UC_REQUIRE(m && cam && oh, "render_camera_host: null argument");
+    if (n_rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    ucnerf_outputs od{};
+    std::vector<OutSlot> slots;
+    if (int e = stage_outputs(m, (size_t)n_rows * cam->width, oh, od, slots)) return e;
+    if (int e = ucnerf_render_camera(m, cam, row0, n_rows, train_frac, &od, stream)) return e;
+    return copy_back_and_check(m, slots, st);
+}
+
 extern "C" int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays* rh, double train_frac,
                                        const ucnerf_outputs* oh, void* stream) {
     UC_REQUIRE(m && rh && oh, "render_rays_host: null argument");
@@ -539,40 +656,11 @@ extern "C" int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const u
     rd.origins = dsts[0]; rd.directions = dsts[1]; rd.viewdirs = dsts[2]; rd.cam_dirs = dsts[3]; rd.rand_vec = dsts[4];
     rd.radii = dsts[5]; rd.near = dsts[6]; rd.far = dsts[7];
     // ---- stage outputs ----
-    const int nl = m->num_levels;
-    struct Slot { float* host; size_t floats; float** dev_field; };
     ucnerf_outputs od{};
-    std::vector<Slot> slots;
-    auto add = [&](float* host, size_t per_ray, float** field) { if (host) slots.push_back({host, N * per_ray, field}); };
-    add(oh->rgb, 3, &od.rgb); add(oh->depth, 1, &od.depth); add(oh->depth_raw, 1, &od.depth_raw); add(oh->acc, 1, &od.acc);
-    add(oh->distance_mean, 1, &od.distance_mean); add(oh->distance_median, 1, &od.distance_median);
-    add(oh->distance_percentile_5, 1, &od.distance_percentile_5); add(oh->distance_percentile_95, 1, &od.distance_percentile_95);
-    for (int l = 0; l < nl; ++l) {
-        add(oh->sdist[l], (size_t)m->lv[l].S + 1, &od.sdist[l]);
-        add(oh->weights[l], (size_t)m->lv[l].S, &od.weights[l]);
-    }
-    add(oh->sample_rgb, (size_t)m->lv[nl - 1].S * 3, &od.sample_rgb);
-    add(oh->sample_density, (size_t)m->lv[nl - 1].S, &od.sample_density);
-    add(oh->packed, 12, &od.packed);
-    size_t tot = 0;
-    for (auto& s : slots) tot += (s.floats + 3) & ~size_t(3);
-    if (int e = m->stage_out.ensure(std::max<size_t>(tot, 4) * sizeof(float))) return e;
-    size_t o2 = 0;
-    for (auto& s : slots) { *s.dev_field = m->stage_out.as<float>() + o2; o2 += (s.floats + 3) & ~size_t(3); }
+    std::vector<OutSlot> slots;
+    if (int e = stage_outputs(m, N, oh, od, slots)) return e;
     if (int e = ucnerf_render_rays(m, n_rays, &rd, train_frac, &od, stream)) return e;
-    for (auto& s : slots)
-        UC_CUDA_OK(cudaMemcpyAsync(s.host, *s.dev_field, s.floats * sizeof(float), cudaMemcpyDeviceToHost, st));
-    UC_CUDA_OK(cudaStreamSynchronize(st));
-    {
-        uint32_t wd[32];
-        if (int e = color_tc_status(wd)) return e;
-        if (wd[0] != 0) {
-            set_error("color_mlp_tc: pipeline watchdog fired (tag " + std::to_string(wd[0]) + ", barrier " +
-                      std::to_string(wd[3]) + ", step " + std::to_string(wd[6]) + ")");
-            return 5;
-        }
-    }
-    return 0;
+    return copy_back_and_check(m, slots, st);
 }
 
 // Watchdog record of the tensor-core colour MLP (synchronises the device): out16[0] != 0 means a pipeline wait

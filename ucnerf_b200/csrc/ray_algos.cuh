@@ -556,4 +556,86 @@ UC_HD void composite_ray(const X& ex, int S, const float* sdist, const float* de
     ex.sync();
 }
 
+// ---- camera -> ray -----------------------------------------------------
+// camera_utils.pixels_to_rays (internal/camera_utils.py:L448-557; perspective, no distortion, no NDC) evaluated as
+// numpy does: float64 arithmetic on float32-valued matrices, results cast to float32 (datasets.py:L476).
+UC_HD double dm(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+UC_HD double da(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+
+struct CameraConst {
+    double pixtocam[9];    // inverse intrinsics, row-major 3x3 (float32 values in the reference's Waymo loader)
+    double rot[9];         // camtoworld[:3,:3], row-major
+    float origin[3];       // camtoworld[:3,3]
+    float cam_dir[3];      // -camtoworld[:3,2]  (datasets.py:L446)
+    float near, far;
+    uint32_t width, height;
+    uint64_t rand_seed;
+};
+
+struct PixelRay {
+    float dir[3], view[3], plane[2], radius;
+};
+
+// direction through pixel centre (x + 0.5, y + 0.5): pixtocam @ [x, y, 1], OpenCV -> OpenGL flip (diag(1,-1,-1)),
+// then camtoworld rotation; sums left to right like the reference's matmuls
+UC_HD void pixel_dir(const CameraConst& c, double px, double py, double (&cam)[3], double (&d)[3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cam[i] = da(da(dm(c.pixtocam[3 * i], px), dm(c.pixtocam[3 * i + 1], py)), c.pixtocam[3 * i + 2]);
+    cam[1] = -cam[1];
+    cam[2] = -cam[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d[i] = da(da(dm(c.rot[3 * i], cam[0]), dm(c.rot[3 * i + 1], cam[1])), dm(c.rot[3 * i + 2], cam[2]));
+}
+UC_HD double dnorm3(const double (&v)[3]) { return sqrt(da(da(dm(v[0], v[0]), dm(v[1], v[1])), dm(v[2], v[2]))); }
+
+UC_HD void pixel_to_ray(const CameraConst& c, int x, int y, PixelRay& r) {
+    double cam[3], d[3], cx[3], dx[3], cy[3], dy[3];
+    pixel_dir(c, (double)x + 0.5, (double)y + 0.5, cam, d);
+    pixel_dir(c, (double)(x + 1) + 0.5, (double)y + 0.5, cx, dx);
+    pixel_dir(c, (double)x + 0.5, (double)(y + 1) + 0.5, cy, dy);
+    const double n = dnorm3(d);
+    const double ex[3] = {da(dx[0], -d[0]), da(dx[1], -d[1]), da(dx[2], -d[2])};
+    const double ey[3] = {da(dy[0], -d[0]), da(dy[1], -d[1]), da(dy[2], -d[2])};
+    // radii = (0.5 * (|dx - d| + |dy - d|)) * 2 / sqrt(12)      camera_utils.py:L548-556
+    const double rad = dm(dm(0.5, da(dnorm3(ex), dnorm3(ey))), 2.0) / 3.4641016151377544;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        r.dir[i] = (float)d[i];
+        r.view[i] = (float)(d[i] / n);
+    }
+    r.plane[0] = (float)cam[0];
+    r.plane[1] = (float)cam[1];
+    r.radius = (float)rad;
+}
+
+// counter-based standard normals (4 per call) for the cone-basis vector: splitmix64 -> two Box-Muller pairs
+UC_HD uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+UC_HD void normal4(uint64_t seed, uint64_t counter, float (&n)[4]) {
+    const uint64_t a = splitmix64(seed ^ splitmix64(counter)), b = splitmix64(a);
+    const float u0 = ((float)(uint32_t)(a >> 40) + 0.5f) * (1.0f / 16777216.0f), u1 = ((float)(uint32_t)((a >> 8) & 0xffffffu)) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(uint32_t)(b >> 40) + 0.5f) * (1.0f / 16777216.0f), u3 = ((float)(uint32_t)((b >> 8) & 0xffffffu)) * (1.0f / 16777216.0f);
+    const float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+    n[0] = r0 * cosf(6.2831853f * u1); n[1] = r0 * sinf(6.2831853f * u1);
+    n[2] = r1 * cosf(6.2831853f * u3); n[3] = r1 * sinf(6.2831853f * u3);
+}
+
 }  // namespace ucnerf

@@ -9,6 +9,11 @@ struct RayPtrs {
     const float *origins, *directions, *viewdirs, *cam_dirs, *radii, *near, *far, *rand_vec;
 };
 
+// outputs of generate_rays_kernel (any of origins / cam_dirs / near / far / imageplane / rand_vec may be NULL)
+struct RayOutPtrs {
+    float *origins, *directions, *viewdirs, *cam_dirs, *radii, *near, *far, *imageplane, *rand_vec;
+};
+
 struct ResampleParams {
     uint32_t n_rays;
     int n_prev;              // bins of the previous level (1 for the first level)
@@ -38,6 +43,7 @@ struct SampleParams {
     float* density;          // [N, S]
     float* h1;               // [N*S, 64] (NeRF level only)
     float g2[16];            // float(grid_sizes[l]^2)
+    int cell_runs;           // 1: level-outer loop with cell-run reuse of the gathered corners (sample_encode.cu)
 };
 
 // Colour MLP with the linear bottleneck layer folded into its two consumers (exact algebra, see model.cu):
@@ -88,6 +94,7 @@ struct CompositeParams {
     float *o_rgb, *o_depth, *o_depth_raw, *o_acc, *o_mean, *o_median, *o_p5, *o_p95, *o_packed;
 };
 
+int launch_generate_rays(const CameraConst& cam, uint32_t row0, uint32_t n_rows, const RayOutPtrs& o, cudaStream_t st);
 int launch_resample(const ResampleParams& p, cudaStream_t st);
 int launch_sample_encode(const SampleParams& p, bool nerf, cudaStream_t st);
 int launch_color_mlp_simt(const ColorParams& p, int np, cudaStream_t st);

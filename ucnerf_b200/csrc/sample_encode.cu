@@ -36,6 +36,15 @@ __device__ __forceinline__ const float4* entry_ptr(uint64_t tab, uint32_t idx) {
     return reinterpret_cast<const float4*>(a);
 }
 
+// 1/sqrt(x) as the single MUFU.RSQ that rsqrtf is built on, without its denormal-input rescaling (3 extra issue slots
+// per point-level): the argument 8 sigma^2 G^2 is >= 1e-12 for any representable cone, and a flushed denormal gives
+// +inf -> erf weight exactly 1, the same value the rescaled form leads to.
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // MODE: 0 dense (index < table size, no reduction), 1 hashed with power-of-two table, 2 generic (runtime flags)
 template <int MODE>
 __device__ __forceinline__ void gather8(const GridLevel& lv, const float4* __restrict__ tab_, const CellCoords& c,
@@ -118,7 +127,17 @@ __device__ __forceinline__ SamplePos sample_pos(size_t q, uint32_t n_rays, int S
 // thread t: hg = t % 4 -> hidden units {hg + 4 jj}, sg = t / 4 -> samples {sg + 32 s}.  h1 is an internal buffer, so
 // it is stored in that permuted column order (column 16 hg + jj <-> hidden unit hg + 4 jj, see kH1Perm in
 // ray_march.cuh) and the consumer's weight rows are permuted to match on the host.
-template <int LMAX, bool NERF, int ND, int MINB, bool REMAP>
+//
+// RUNS = true ("cell-run reuse"): the six multisample points of an interval are ordered along the ray and, on the
+// coarse levels, mostly fall into the SAME grid cell (measured on the waymo.gin frame: 93 / 86 / 75 / 63 / 48 / 30 %
+// of the proposal samples have all six points in one cell on levels 0..5; 9.9 distinct cells per sample instead of
+// 36 point-levels).  The loop nest is therefore level-outer / point-inner: the six grid coordinates stay in
+// registers, and the 8 corner entries of a level are re-gathered only when a point enters a different cell than its
+// predecessor.  Interpolation, erf pooling and the summation order over the six points are unchanged, so results
+// are bit-identical to the RUNS = false form; only redundant gathers (L1 wavefronts, the limiter) disappear.  The
+// level loop is rolled (per-level constants by dynamic constant-bank index), pooled features go straight to the
+// shared-memory rows the density layer reads.
+template <int LMAX, bool NERF, int ND, int MINB, bool REMAP, bool RUNS>
 __global__ void __launch_bounds__(kSampleThreads, MINB)
 sample_encode_kernel(const __grid_constant__ SampleParams p) {
     constexpr int LC = LMAX * 4;
@@ -127,7 +146,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
     float* sW1 = smem_dyn;                       // [64][LDS]
     float* sB1 = sW1 + 64 * LDS;                 // [64]
     float* sW2 = sB1 + 64;                       // [64]
-    float* sF = sW2 + 64;                        // [128][LDS], only allocated for the re-mapped MLP phase
+    float* sF = sW2 + 64;                        // [128][LDS], only allocated for the re-mapped MLP phase / RUNS
     (void)sF;
     for (int i = threadIdx.x; i < 64 * LMAX; i += kSampleThreads) {
         const int j = i / LMAX, k4 = i - j * LMAX;
@@ -145,6 +164,77 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
 #pragma unroll
     for (int i = 0; i < LMAX * 2; ++i) F2[i] = make_float2(0.f, 0.f);
 
+    if constexpr (RUNS) {
+        float* myF = sF + threadIdx.x * LDS;
+        int L = 0;
+        if (me.valid) {
+            const uint32_t ray = me.ray;
+            const int s = me.s;
+            float gq[6][3], s8q[6];
+            uint32_t inmask = 0;
+            {
+                RayGeom rg;
+                make_ray_geom(rg, p.rays.origins + 3 * (size_t)ray, p.rays.directions + 3 * (size_t)ray,
+                              p.rays.cam_dirs + 3 * (size_t)ray, p.rays.rand_vec + 3 * (size_t)ray, p.rays.radii[ray],
+                              p.rays.near[ray], p.rays.far[ray]);
+                const float s0 = p.sdist[(size_t)ray * p.sdist_stride + s];
+                const float s1 = p.sdist[(size_t)ray * p.sdist_stride + s + 1];
+                const float t0 = fa(fm(s0, rg.far), fm(fs(1.f, s0), rg.near));
+                const float t1 = fa(fm(s1, rg.far), fm(fs(1.f, s1), rg.near));
+                const ConeInterval ci = make_cone_interval(t0, t1);
+                const int odd = s & 1;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    float sigma;
+                    cone_point(rg, ci, p.cone, j, odd, p.std_scale, gq[j], sigma);
+                    s8q[j] = fm(8.f, fm(sigma, sigma));
+                    // gridencoder.cu:L110-135: out-of-range input -> zero features for every level
+                    const bool oob = gq[j][0] < 0.f || gq[j][0] > 1.f || gq[j][1] < 0.f || gq[j][1] > 1.f || gq[j][2] < 0.f || gq[j][2] > 1.f;
+                    if (!oob) inmask |= 1u << j;
+                }
+            }
+            L = p.grid.num_levels;
+#pragma unroll 1
+            for (int l = 0; l < L; ++l) {
+                const GridLevel& lv = p.grid.lv[l];
+                const float4* tab = p.grid.table + lv.offset;
+                const float g2l = p.g2[l];
+                float4 v[8];
+                uint32_t pix = 0xffffffffu, piy = 0, piz = 0;   // no cell has ix = 2^32 - 1: the first in-range point always gathers
+                float2 Fxy = make_float2(0.f, 0.f), Fzw = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    if ((inmask >> j) & 1u) {
+                        const CellCoords c = cell_of(lv, gq[j]);
+                        if (c.ix != pix || c.iy != piy || c.iz != piz) {
+                            if (!lv.hashed) gather8<0>(lv, tab, c, v);
+                            else if (lv.mod_mode == 1) gather8<1>(lv, tab, c, v);
+                            else gather8<2>(lv, tab, c, v);
+                            pix = c.ix; piy = c.iy; piz = c.iz;
+                        }
+                        const Feat4 r = interp8(c, v);
+                        const float ea = rsqrt_fast(fm(s8q[j], g2l));       // models.py:L495, see the RUNS = false form below
+                        const float om = ea >= 4.f ? 1.f : erff(ea);
+                        const float2 om2 = make_float2(om, om);
+                        Fxy = ffma2(om2, r.xy, Fxy);
+                        Fzw = ffma2(om2, r.zw, Fzw);
+                    }
+                }
+                // .mean(dim=-3) over the 6 points, models.py:L496
+                *reinterpret_cast<float4*>(myF + 4 * l) =
+                    make_float4(Fxy.x * 0.16666667f, Fxy.y * 0.16666667f, Fzw.x * 0.16666667f, Fzw.y * 0.16666667f);
+            }
+        }
+        for (int l = L; l < LMAX; ++l) *reinterpret_cast<float4*>(myF + 4 * l) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (!REMAP) {
+#pragma unroll
+            for (int l = 0; l < LMAX; ++l) {
+                const float4 f = *reinterpret_cast<const float4*>(myF + 4 * l);
+                F2[2 * l] = make_float2(f.x, f.y);   // own row: already the mean over the six points
+                F2[2 * l + 1] = make_float2(f.z, f.w);
+            }
+        }
+    } else
     if (me.valid) {
         const uint32_t ray = me.ray;
         const int s = me.s;
@@ -182,7 +272,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
                     const Feat4 r = interp8(c, v);
                     // models.py:L495 scale-aware down-weighting erf(1/sqrt(8 std^2 G^2));
                     // erf(x) rounds to exactly 1.0f for x >= 4, so coarse levels skip the evaluation
-                    const float ea = rsqrtf(fm(s8, p.g2[l]));
+                    const float ea = rsqrt_fast(fm(s8, p.g2[l]));
                     const float om = ea >= 4.f ? 1.f : erff(ea);
                     const float2 om2 = make_float2(om, om);
                     F2[2 * l] = ffma2(om2, r.xy, F2[2 * l]);
@@ -195,9 +285,11 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
         // thread-per-sample density layer (weights as broadcast LDS.128); used where the re-mapped phase does not pay
         __syncthreads();  // weights staged
         if (!me.valid) return;
-        const float2 sixth = make_float2(0.16666667f, 0.16666667f);
+        if constexpr (!RUNS) {
+            const float2 sixth = make_float2(0.16666667f, 0.16666667f);
 #pragma unroll
-        for (int i = 0; i < LMAX * 2; ++i) F2[i] = fmul2(F2[i], sixth);  // .mean(dim=-3) over the 6 points, models.py:L496
+            for (int i = 0; i < LMAX * 2; ++i) F2[i] = fmul2(F2[i], sixth);  // .mean(dim=-3) over the 6 points, models.py:L496
+        }
         float raw = p.b2;
         float* hrow = NERF ? p.h1 + idx * 64 : nullptr;
 #pragma unroll 4
@@ -224,11 +316,13 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
         return;
     }
     // .mean(dim=-3) over the 6 points (models.py:L496), parked in shared memory for the re-mapped MLP phase
+    if constexpr (!RUNS) {
 #pragma unroll
-    for (int l = 0; l < LMAX; ++l)
-        *reinterpret_cast<float4*>(sF + threadIdx.x * LDS + 4 * l) =
-            make_float4(F2[2 * l].x * 0.16666667f, F2[2 * l].y * 0.16666667f, F2[2 * l + 1].x * 0.16666667f,
-                        F2[2 * l + 1].y * 0.16666667f);
+        for (int l = 0; l < LMAX; ++l)
+            *reinterpret_cast<float4*>(sF + threadIdx.x * LDS + 4 * l) =
+                make_float4(F2[2 * l].x * 0.16666667f, F2[2 * l].y * 0.16666667f, F2[2 * l + 1].x * 0.16666667f,
+                            F2[2 * l + 1].y * 0.16666667f);
+    }
     __syncthreads();
 
     // density_layer: Linear(L*C,64) -> ReLU -> Linear(64, .)[0]   (models.py:L438-441, L507-508)
@@ -309,31 +403,33 @@ static int dense_prefix(const GridDesc& g) {
     return nd;
 }
 
-template <int LMAX, bool NERF, int ND, int MINB>
+template <int LMAX, bool NERF, int ND, int MINB, bool RUNS>
 static int launch_one_impl(const SampleParams& p, cudaStream_t st) {
     const size_t total = (size_t)div_up(p.n_rays, 32u) * 32u * (size_t)p.S;  // ray groups of 32, see sample_pos
     const unsigned blocks = (unsigned)div_up(total, (size_t)kSampleThreads);
     // measured on B200 (profiles/r1_summary.md): the re-mapped density layer pays on the proposal level only
     constexpr bool kRemap = UC_REMAP_PROP ? !NERF : false;
-    constexpr size_t smem = sizeof(float) * ((64 + (kRemap ? kSampleThreads : 0)) * (LMAX * 4 + 4) + 128);
+    constexpr size_t smem = sizeof(float) * ((64 + ((kRemap || RUNS) ? kSampleThreads : 0)) * (LMAX * 4 + 4) + 128);
     if constexpr (smem > 48 * 1024) {
         static bool configured = false;
         if (!configured) {
-            UC_CUDA_OK(cudaFuncSetAttribute(sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap>,
+            UC_CUDA_OK(cudaFuncSetAttribute(sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap, RUNS>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = true;
         }
     }
-    sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap><<<blocks, kSampleThreads, smem, st>>>(p);
+    sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap, RUNS><<<blocks, kSampleThreads, smem, st>>>(p);
     UC_LAUNCH_CHECK();
     return 0;
 }
 
 template <int LMAX, bool NERF, int ND, int MINB>
-static int launch_one(const SampleParams& p, cudaStream_t st) { return launch_one_impl<LMAX, NERF, ND, MINB>(p, st); }
+static int launch_one(const SampleParams& p, cudaStream_t st) { return launch_one_impl<LMAX, NERF, ND, MINB, false>(p, st); }
 
 template <int LMAX, int MINB>
 static int launch_lmax(const SampleParams& p, bool nerf, int nd, cudaStream_t st) {
+    if (p.cell_runs)  // level loop rolled: one instantiation per (LMAX, level kind)
+        return nerf ? launch_one_impl<LMAX, true, -1, MINB, true>(p, st) : launch_one_impl<LMAX, false, -1, MINB, true>(p, st);
     if (nd == 3) return nerf ? launch_one<LMAX, true, 3, MINB>(p, st) : launch_one<LMAX, false, 3, MINB>(p, st);
     if constexpr (LMAX == 4) {
         if (nd == 1) return nerf ? launch_one<LMAX, true, 1, MINB>(p, st) : launch_one<LMAX, false, 1, MINB>(p, st);

@@ -32,6 +32,45 @@ def _grid_num_levels(desired, base=16, interval=2):
     return int(np.log(desired / base) / np.log(interval)) + 1
 
 
+def make_camera(pixtocam, camtoworld, width: int, height: int, near: float, far: float, rand_seed: int = 0):
+    """ucnerf_camera from the arrays the reference's Dataset holds (`pixtocams[i]` [3,3], `camtoworlds[i]` [3,4] or
+    [4,4], `width`, `height`, `near`, `far`; internal/datasets.py:L296-348)."""
+    cam = _lib.Camera()
+    p = np.asarray(pixtocam, dtype=np.float64).reshape(3, 3)
+    c = np.asarray(camtoworld, dtype=np.float64)[:3, :4]
+    cam.pixtocam[:] = p.reshape(-1).tolist()
+    cam.camtoworld[:] = np.ascontiguousarray(c).reshape(-1).tolist()
+    cam.width, cam.height, cam.near, cam.far, cam.rand_seed = int(width), int(height), float(near), float(far), int(rand_seed)
+    return cam
+
+
+def generate_rays(pixtocam, camtoworld, width, height, near, far, rows=None, rand_seed=0, device=None,
+                  with_rand_vec=True) -> Dict[str, torch.Tensor]:
+    """GPU replacement of the eval loader's numpy ray generation (camera_utils.pixels_to_rays / cast_pinhole_rays,
+    internal/camera_utils.py:L448-557,L611-632 + Dataset._make_ray_batch, datasets.py:L386-476) for one perspective
+    camera without lens distortion: returns the reference's ray-dict keys as flat CUDA tensors for image rows
+    `rows=(row0, n_rows)` (default: the whole image), row-major pixel order."""
+    if not torch.cuda.is_available():
+        raise _lib.UcnerfError("ucnerf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    row0, n_rows = rows if rows is not None else (0, height)
+    n = n_rows * width
+    cam = make_camera(pixtocam, camtoworld, width, height, near, far, rand_seed)
+    shapes = {"origins": 3, "directions": 3, "viewdirs": 3, "cam_dirs": 3, "radii": 1, "near": 1, "far": 1,
+              "imageplane": 2}
+    if with_rand_vec:
+        shapes["rand_vec"] = 3
+    out = {k: torch.empty((n, w), device=dev, dtype=torch.float32) for k, w in shapes.items()}
+    rb = _lib.RayBuffers()
+    for k, t in out.items():
+        setattr(rb, k, t.data_ptr())
+    with torch.cuda.device(dev):
+        _lib.check(lib.ucnerf_generate_rays(C.byref(cam), row0, n_rows, C.byref(rb),
+                                            torch.cuda.current_stream().cuda_stream), "generate_rays")
+    return out
+
+
 class HotPathModel:
     """B200 renderer for one UC-NeRF `Model` (proposal MLPs + NeRF MLP, waymo.gin-style)."""
 
@@ -247,6 +286,32 @@ class HotPathModel:
                                                   torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "render_rays_host")
         return out
+
+    def render_camera(self, pixtocam, camtoworld, width, height, near, far, rows=None, train_frac: float = 1.0,
+                      rand_seed: int = 0, want=("rgb", "depth", "acc"), host_out: Optional[Dict[str, torch.Tensor]] = None):
+        """Render image rows `rows=(row0, n_rows)` (default all) of one pinhole camera: the ray batch is generated on
+        the GPU from the camera parameters (ucnerf_render_camera).  With `host_out` (dict of pinned CPU tensors, or
+        True to allocate them) the results are copied back inside the call (ucnerf_render_camera_host)."""
+        row0, n_rows = rows if rows is not None else (0, height)
+        n = n_rows * width
+        cam = make_camera(pixtocam, camtoworld, width, height, near, far, rand_seed)
+        spec = self._out_spec(n, want)
+        o = _lib.Outputs()
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            if host_out is not None and host_out is not False:
+                if host_out is True:
+                    host_out = {k: torch.empty(shape, dtype=torch.float32, pin_memory=True) for k, shape in spec.items()}
+                self._fill_struct(o, host_out)
+                rc = self.lib.ucnerf_render_camera_host(self._handle, C.byref(cam), row0, n_rows, float(train_frac),
+                                                        C.byref(o), st)
+                _lib.check(rc, "render_camera_host")
+                return host_out
+            bufs = {k: torch.empty(shape, device=self.device, dtype=torch.float32) for k, shape in spec.items()}
+            self._fill_struct(o, bufs)
+            rc = self.lib.ucnerf_render_camera(self._handle, C.byref(cam), row0, n_rows, float(train_frac), C.byref(o), st)
+        _lib.check(rc, "render_camera")
+        return bufs
 
     def forward(self, rand, batch, train_frac, compute_extras, zero_glo=True, eval_camidx=None, rand_vec=None):
         """`Model.forward` contract for the eval path (internal/models.py:L97-365, heads excluded):

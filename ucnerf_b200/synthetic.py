@@ -103,6 +103,23 @@ def synthetic_state_dict(wl: Workload, seed=0, emb_range=0.5) -> Dict[str, torch
     return sd
 
 
+def pinhole_camera(height, width, seed=0, near=0.0, far=8.0, focal=None):
+    """(pixtocam, camtoworld, width, height, near, far) of the synthetic camera `pinhole_rays(seed)` uses, as float32
+    values like the reference's Waymo loader holds them (datasets.py:L672,L855-857)."""
+    rng = np.random.default_rng(seed)
+    focal = focal or 2000.0 * width / 1920.0
+    q = rng.standard_normal(4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    origin = rng.uniform(-0.1, 0.1, 3)
+    K = np.array([[focal, 0, width * 0.5], [0, focal, height * 0.5], [0, 0, 1]], dtype=np.float32)
+    pose = np.concatenate([R, origin[:, None]], 1).astype(np.float32)
+    return np.linalg.inv(K), pose, width, height, near, far
+
+
 def pinhole_rays(height, width, seed=0, near=0.0, far=8.0, focal=None) -> Dict[str, torch.Tensor]:
     """One pinhole camera inside the scene (OpenGL convention, looks along -z of a random pose): flat [H*W, .] CPU
     tensors with the reference's ray-dict keys + the cone-basis `rand_vec` (render.py:L140)."""

@@ -291,3 +291,30 @@ def test_render_edge_scenes_match_oracle(bias_shift, label):
     if label == "opaque":
         assert int((hist[0]["weights"] == 0).sum()) > 0 and acc.min() > 0.99  # exact-zero weights: -inf logits path
     r.close()
+
+
+def test_resample_kernel_matches_cpu_instantiation_on_concentrated_histogram(harness, lib):
+    """The warp-per-ray resample kernel against the serial instantiation of the same template on a level-2 input of
+    the three_level case (concentrated proposal histogram: the galloping searches take their long paths here; an
+    earlier formulation of that search was mis-executed on the GPU while the CPU instantiation was right)."""
+    import ctypes
+    d = load_golden("resample_three_level_l2")
+    t_prev, w_prev, dil = d["all_t"], d["all_w"], float(d["dil"])
+    n, n_prev = w_prev.shape
+    S = 32
+    pad = 1 / (2 * S)
+    u = torch.linspace(pad, 1. - pad - O.EPS, S).numpy().copy()
+    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    ref = np.zeros((n, S + 1), np.float32)
+    harness.h_resample(n, n_prev, fp(t_prev), fp(w_prev), 1, ctypes.c_float(dil), ctypes.c_float(1), ctypes.c_float(0), S,
+                       fp(u), fp(ref))
+    tg, wg = torch.from_numpy(t_prev).cuda(), torch.from_numpy(w_prev).cuda()
+    out = torch.zeros((n, S + 1), device="cuda")
+    lib.ucnerf_debug_resample.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+    rc = lib.ucnerf_debug_resample(n, n_prev, tg.data_ptr(), wg.data_ptr(), 1, dil, 1.0, 0.0, S, out.data_ptr(), None, 0, None)
+    assert rc == 0, lib.ucnerf_last_error()
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() < 2e-6
+    assert np.all(np.diff(got, axis=1) >= 0)

@@ -50,16 +50,24 @@ constexpr int kStages = 2;
 constexpr uint32_t kSmemA = 0;
 constexpr uint32_t kSmemB = kSmemA + kStages * kASlotBytes;            // 65536
 constexpr uint32_t kSmemMisc = kSmemB + kStages * kBSlotBytes;         // 196608
-// misc region: barriers (16 x 8 B), tmem ptr, then c0[256], c1[256], R[256] float4, r0[4]
+// misc region: barriers (NUM_BARS x 8 B), tmem ptr, then c0[256], c1[256], R[256] float4, r0[4]
 constexpr uint32_t kOffBar = 0;
-constexpr uint32_t kOffTmem = 128;
+constexpr uint32_t kOffTmem = 192;
 constexpr uint32_t kOffC0 = 256;
 constexpr uint32_t kOffC1 = kOffC0 + 1024;
 constexpr uint32_t kOffR = kOffC1 + 1024;
 constexpr uint32_t kOffR0 = kOffR + 4096;
 constexpr uint32_t kOffPart = kOffR0 + 16;          // [128] float4: rgb partial sums handed from group 1 to group 0
 constexpr uint32_t kMiscBytes = kOffPart + 2048;
-constexpr uint32_t kSmemTotal = kSmemMisc + kMiscBytes + 1024;  // +1024: manual 1 KB alignment slack
+// per-tile staging of the per-ray bias rows (dir_bias, 2 KB per ray): a 128-row tile touches at most kBiasRays rays
+// when S >= 32; two stages, filled by the loader thread with one bulk copy per tile (the rows of consecutive rays are
+// contiguous), so the producer groups read their biases from shared memory instead of waiting on L2 / HBM latency
+// six times per tile
+constexpr int kBiasRays = 5;
+constexpr uint32_t kBiasStageBytes = kBiasRays * 2048;
+constexpr uint32_t kSmemBias = kSmemMisc + ((kMiscBytes + 127) & ~127u);
+constexpr uint32_t kSmemTotal = kSmemBias + 2 * kBiasStageBytes + 1024;  // +1024: manual 1 KB alignment slack
+static_assert(kSmemTotal <= 232448, "shared memory budget");
 constexpr int kThreads = 320;                     // warps 0-3 / 4-7: producer groups, 8: MMA, 9: weight loader
 constexpr int kMmaWarp = 8;
 
@@ -68,7 +76,8 @@ constexpr int kMmaWarp = 8;
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
 enum Bar { A_FULL0 = 0, A_FULL1, A_EMPTY0, A_EMPTY1, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, ACC3_FULL, ACC4_FULL,
-           ACC3_EMPTY, ACC4_EMPTY, PART_FULL, PART_EMPTY, NUM_BARS };
+           ACC3_EMPTY, ACC4_EMPTY, PART_FULL, PART_EMPTY, BIAS_FULL0, BIAS_FULL1, BIAS_EMPTY0, BIAS_EMPTY1, NUM_BARS };
+static_assert(NUM_BARS * 8 <= kOffTmem, "barrier block overlaps the TMEM pointer slot");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -247,6 +256,8 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         mbar_init(BAR(ACC3_FULL), 1); mbar_init(BAR(ACC4_FULL), 1);
         mbar_init(BAR(ACC3_EMPTY), 256); mbar_init(BAR(ACC4_EMPTY), 256);
         mbar_init(BAR(PART_FULL), 128); mbar_init(BAR(PART_EMPTY), 128);
+        mbar_init(BAR(BIAS_FULL0), 1); mbar_init(BAR(BIAS_FULL1), 1);
+        mbar_init(BAR(BIAS_EMPTY0), 256); mbar_init(BAR(BIAS_EMPTY1), 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {  // whole warp: allocate all 512 TMEM columns
@@ -261,6 +272,10 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     const uint32_t ntiles = (p.n_rows + kTileM - 1) / kTileM;
+    // staged per-ray biases need a tile to span <= kBiasRays rays: S >= 32 (else the global-memory path is used)
+    const bool smem_bias = p.S >= 32 && !(p.debug_flags & 16u);
+    const uint32_t n_rays_total = p.n_rows / (uint32_t)p.S;
+    const uint8_t* sBias = smem + kSmemBias;
 
     if (warp < 8) {
         // ================= producer / epilogue warpgroups: thread <-> row t of the tile ================
@@ -283,8 +298,16 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
             float o0 = 0.f, o1 = 0.f, o2 = 0.f;
             const float k1 = p.k1;
             const uint32_t erow = tl * kTileM + t;
-            const float4* bias1 = reinterpret_cast<const float4*>(
-                p.dir_bias + (size_t)((erow < p.n_rows ? erow : 0u) / (uint32_t)p.S) * 512 + 256 + g * 128);
+            const uint32_t eray = (erow < p.n_rows ? erow : 0u) / (uint32_t)p.S;
+            const float4* bias1;
+            if (smem_bias) {
+                if (!mbar_wait(BAR(BIAS_FULL0 + (itp & 1)), (itp >> 1) & 1, p.dbg, 11, BIAS_FULL0 + (itp & 1), itp, 99)) return false;
+                const uint32_t f = (tl * kTileM) / (uint32_t)p.S;
+                const uint32_t lr = eray >= f ? min(eray - f, (uint32_t)kBiasRays - 1) : 0u;
+                bias1 = reinterpret_cast<const float4*>(sBias + (itp & 1) * kBiasStageBytes + lr * 2048 + 1024 + g * 512);
+            } else {
+                bias1 = reinterpret_cast<const float4*>(p.dir_bias + (size_t)eray * 512 + 256 + g * 128);
+            }
             // software pipeline: the TMEM load of the next 32 columns is in flight while the current ones are consumed
             uint32_t ra[32], rb[32];
             tmem_ld32_issue(lane_taddr + (uint32_t)(256 + g * 128), ra);
@@ -292,7 +315,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
             for (int jj = 0; jj < 4; ++jj) {
                 float4 bb[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) bb[q] = __ldg(bias1 + 8 * jj + q);
+                for (int q = 0; q < 8; ++q) bb[q] = smem_bias ? bias1[8 * jj + q] : __ldg(bias1 + 8 * jj + q);
                 tmem_ld_wait();
                 uint32_t (&cur)[32] = (jj & 1) ? rb : ra;
                 uint32_t (&nxt)[32] = (jj & 1) ? ra : rb;
@@ -313,6 +336,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
             }
             tc_fence_before();
             mbar_arrive(BAR(ACC4_EMPTY));
+            if (smem_bias) mbar_arrive(BAR(BIAS_EMPTY0 + (itp & 1)));   // last read of this tile's staged biases
             if (g == 1) {
                 if (!mbar_wait(BAR(PART_EMPTY), (itp & 1) ^ 1, p.dbg, 9, PART_EMPTY, itp, 99)) return false;
                 sPart[t] = make_float4(o0, o1, o2, 0.f);
@@ -336,7 +360,13 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
             const uint32_t row = tile * kTileM + t;
             const bool valid = row < p.n_rows;
             const float* h1row = p.h1 + (size_t)(valid ? row : 0) * 64;
-            const float* bias0 = p.dir_bias + (size_t)((valid ? row : 0u) / (uint32_t)p.S) * 512;  // per-ray [c0' | c1'] rows
+            const uint32_t ray = (valid ? row : 0u) / (uint32_t)p.S;
+            const float* bias0 = p.dir_bias + (size_t)ray * 512;  // per-ray [c0' | c1'] rows
+            if (smem_bias) {
+                const uint32_t f = (tile * kTileM) / (uint32_t)p.S;
+                const uint32_t lr = ray >= f ? min(ray - f, (uint32_t)kBiasRays - 1) : 0u;
+                bias0 = reinterpret_cast<const float*>(sBias + (it & 1) * kBiasStageBytes + lr * 2048);
+            }
 #pragma unroll 1
             for (int c = g; c < kSteps; c += 2) {
                 const long long tc0 = prof ? clock64() : 0;
@@ -375,6 +405,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                     if (j < 2) {  // first TMEM chunk of this group for this tile
                         const long long ta = prof ? clock64() : 0;
                         if (!mbar_wait(BAR(ACC3_FULL), it & 1, p.dbg, 1, ACC3_FULL, it, c)) goto teardown;
+                        if (smem_bias && !mbar_wait(BAR(BIAS_FULL0 + (it & 1)), (it >> 1) & 1, p.dbg, 12, BIAS_FULL0 + (it & 1), it, c)) goto teardown;
                         if (prof) { tw = clock64() - ta; pw_acc3 += tw; }
                         tc_fence_after();
                     }
@@ -384,7 +415,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                     const float4* b0 = reinterpret_cast<const float4*>(bias0 + 64 * j);
                     float4 bb[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) bb[q] = __ldg(b0 + q);  // overlaps the TMEM loads
+                    for (int q = 0; q < 8; ++q) bb[q] = smem_bias ? b0[q] : __ldg(b0 + q);  // overlaps the TMEM loads
                     tmem_ld_wait();
                     if (j >= 2) {  // this group's part of acc3 is in registers
                         tc_fence_before();
@@ -399,7 +430,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                         float v[32];
                         if (hf) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) bb[q] = __ldg(b0 + 8 + q);
+                            for (int q = 0; q < 8; ++q) bb[q] = smem_bias ? b0[8 + q] : __ldg(b0 + 8 + q);
                         }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -491,6 +522,19 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         if (lane == 0) {
             uint32_t slot = 0, phase = 0, it = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                if (smem_bias) {
+                    // bias rows of the rays this tile touches: one contiguous bulk copy into stage it & 1
+                    const uint32_t st2 = it & 1;
+                    if (!mbar_wait(BAR(BIAS_EMPTY0 + st2), ((it >> 1) & 1) ^ 1, p.dbg, 13, BIAS_EMPTY0 + st2, it, 0)) goto teardown;
+                    const uint32_t f = (tile * kTileM) / (uint32_t)p.S;
+                    uint32_t l = (tile * kTileM + kTileM - 1) / (uint32_t)p.S;
+                    if (l >= n_rays_total) l = n_rays_total - 1;
+                    uint32_t cnt = l - f + 1;
+                    if (cnt > (uint32_t)kBiasRays) cnt = kBiasRays;
+                    mbar_expect_tx(BAR(BIAS_FULL0 + st2), cnt * 2048);
+                    bulk_g2s(smem_u32(sBias + st2 * kBiasStageBytes), p.dir_bias + (size_t)f * 512, cnt * 2048,
+                             BAR(BIAS_FULL0 + st2));
+                }
 #pragma unroll 1
                 for (int s = 0; s < kSteps; ++s) {
                     if (!mbar_wait(BAR(B_EMPTY0 + slot), phase ^ 1, p.dbg, 8, B_EMPTY0 + slot, it, s)) goto teardown;

@@ -670,6 +670,26 @@ extern "C" int ucnerf_debug_tc_status(uint32_t* out16) {
     return color_tc_status(out16);
 }
 
+// Debug entry: one resampling level on device arrays (the kernel of the render path); scratch_out (device, may be NULL)
+// receives the shared-memory scratch of ray `dbg_ray`: [tp (n+1) | pp (n) | T (3n+1) | W (3n+1) | CW (3n+2) | C (S)].
+extern "C" int ucnerf_debug_resample(uint32_t n_rays, int n_prev, const float* t_prev, const float* w_prev, int dilate,
+                                     float dilation, float anneal, float padding, int S, float* out_sdist,
+                                     float* scratch_out, uint32_t dbg_ray, void* stream) {
+    std::vector<float> u(S);
+    deterministic_u(S, u.data());
+    float* du = nullptr;
+    UC_CUDA_OK(cudaMalloc(&du, S * sizeof(float)));
+    UC_CUDA_OK(cudaMemcpy(du, u.data(), S * sizeof(float), cudaMemcpyHostToDevice));
+    ResampleParams rs{};
+    rs.n_rays = n_rays; rs.n_prev = n_prev; rs.t_prev = t_prev; rs.t_prev_stride = (uint32_t)(n_prev + 1); rs.w_prev = w_prev;
+    rs.dilate = dilate; rs.dilation = dilation; rs.anneal = anneal; rs.padding = padding; rs.S = S; rs.u = du;
+    rs.out_sdist = out_sdist; rs.dbg_scratch = scratch_out; rs.dbg_ray = dbg_ray;
+    int e = launch_resample(rs, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(du);
+    return e;
+}
+
 // ---- small host-only helpers exported for the CPU test-suite (no GPU needed) ---------------------
 extern "C" int ucnerf_debug_u_grid(int S, float* out_host) {
     UC_REQUIRE(S >= 1 && out_host, "debug_u_grid: bad argument");

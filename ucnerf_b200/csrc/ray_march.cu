@@ -23,6 +23,11 @@ resample_kernel(const ResampleParams p) {
     const float* wprev = p.w_prev ? p.w_prev + (size_t)ray * p.n_prev : nullptr;
     resample_ray(ex, p.n_prev, tprev, wprev, p.dilate != 0, p.dilation, p.anneal, p.padding, p.S, p.u, sc,
                  p.out_sdist + (size_t)ray * (p.S + 1));
+    if (p.dbg_scratch && ray == p.dbg_ray) {
+        __syncwarp();
+        const float* base = smem + (size_t)warp * ResampleScratch::floats(p.n_prev, p.S);
+        for (int i = ex.lane; i < (int)ResampleScratch::floats(p.n_prev, p.S); i += 32) p.dbg_scratch[i] = base[i];
+    }
 }
 
 int launch_resample(const ResampleParams& p, cudaStream_t st) {

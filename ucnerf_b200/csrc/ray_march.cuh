@@ -25,6 +25,8 @@ struct ResampleParams {
     int S;
     const float* u;          // [S]
     float* out_sdist;        // [N, S+1]
+    float* dbg_scratch;      // debugging: scratch arrays of ray dbg_ray after the call (NULL in production)
+    uint32_t dbg_ray;
 };
 
 struct SampleParams {

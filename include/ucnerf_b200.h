@@ -208,6 +208,14 @@ uint64_t ucnerf_launch_count(void);
  * tensor cores whenever the MLP widths allow, the default), "timing" (see ucnerf_get_timing). */
 int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value);
 
+/* Brightness-correction head folded into the compositing epilogue.  The reference evaluates
+ * BrightnessCorrection (extrinsic_optimizer.py:L4-25: latent code -> 3x256 MLP -> 3x4 affine) once PER RAY for the
+ * single camera index of an eval image and applies rgb <- A[:3,:3] rgb + A[:3,3] to the rendered colour
+ * (models.py:L339-363).  Here the caller evaluates the head once per image and passes the affine (row-major [3][4],
+ * HOST pointer); every following render applies it to the final level's rgb (also inside `packed`).  NULL switches it
+ * off.  The sky branch of that code (model_sky=True) is not part of the fused path. */
+int ucnerf_set_rgb_affine(ucnerf_model* m, const float* affine12_host);
+
 /* Timing probe: with option "timing" != 0, ucnerf_render_rays records a CUDA event pair around every kernel
  * launch on the launch stream (no synchronisation is added).  ucnerf_get_timing waits for the recorded events
  * and returns accumulated device milliseconds and launch counts per kernel family:

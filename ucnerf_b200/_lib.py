@@ -91,6 +91,7 @@ EXPORTS = [
     "ucnerf_grad_total_variation", "ucnerf_model_create", "ucnerf_model_refresh", "ucnerf_model_destroy",
     "ucnerf_render_rays", "ucnerf_render_rays_host", "ucnerf_launch_count", "ucnerf_set_option",
     "ucnerf_get_timing", "ucnerf_generate_rays", "ucnerf_render_camera", "ucnerf_render_camera_host",
+    "ucnerf_set_rgb_affine",
 ]
 
 _lib = None
@@ -128,6 +129,7 @@ def load():
     lib.ucnerf_generate_rays.argtypes = [C.POINTER(Camera), u32, u32, C.POINTER(RayBuffers), vp]
     lib.ucnerf_render_camera.argtypes = [vp, C.POINTER(Camera), u32, u32, C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_render_camera_host.argtypes = [vp, C.POINTER(Camera), u32, u32, C.c_double, C.POINTER(Outputs), vp]
+    lib.ucnerf_set_rgb_affine.argtypes = [vp, vp]
     lib.ucnerf_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.ucnerf_get_timing.argtypes = [vp, c_float_p, C.POINTER(C.c_uint32), C.c_int]
     lib.ucnerf_debug_u_grid.argtypes = [C.c_int, vp]

@@ -78,6 +78,8 @@ struct ucnerf_model {
     DevBuf stage_in, stage_out, cam_rays;
     int64_t chunk_rays = 131072;
     int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 FP16 split (error if shapes unsupported), 2 = auto
+    bool use_affine = false;
+    float affine[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};   // BrightnessCorrection affine of the current image (row-major 3x4)
     int encode_runs = 0;  // cell-run reuse in sample_encode_kernel (bit 0 = proposal levels, bit 1 = NeRF level): measured
                           // slower on B200 (profiles/r1_summary.md), kept as an option
     bool timing = false;
@@ -425,6 +427,8 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
             cq.o_p95 = o.distance_percentile_95 ? o.distance_percentile_95 + ray0 : nullptr;
             cq.o_packed = o.packed ? o.packed + 12 * ray0 : nullptr;
             cq.extras = (cq.o_mean || cq.o_median || cq.o_p5 || cq.o_p95 || cq.o_packed) ? 1 : 0;
+            cq.use_affine = m->use_affine ? 1 : 0;
+            std::memcpy(cq.affine, m->affine, sizeof(cq.affine));
         } else {
             cq.extras = 0;
         }
@@ -487,6 +491,14 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
     else if (k == "timing") m->timing = value != 0;
     else if (k == "tc_debug") m->tc_debug = (uint32_t)value;  // profiling experiments (results invalid when != 0)
     else { set_error("set_option: unknown key " + k); return 1; }
+    return 0;
+}
+
+extern "C" int ucnerf_set_rgb_affine(ucnerf_model* m, const float* affine12_host) {
+    UC_REQUIRE(m, "set_rgb_affine: null model");
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->use_affine = affine12_host != nullptr;
+    if (affine12_host) std::memcpy(m->affine, affine12_host, sizeof(m->affine));
     return 0;
 }
 

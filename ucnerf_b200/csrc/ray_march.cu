@@ -263,6 +263,14 @@ composite_kernel(const CompositeParams p) {
                   p.rgb ? p.rgb + (size_t)ray * p.S * 3 : nullptr, dir, p.rays.near[ray], p.rays.far[ray], p.bg,
                   p.extras != 0, sc, p.weights + (size_t)ray * p.S, ro);
     if (ex.lane == 0) {
+        if (p.use_affine) {
+            // brightness correction (models.py:L349): rgb <- A[:3,:3] rgb + A[:3,3], one affine per image at eval
+            // (extrinsic_optimizer.py:L15-25 evaluated once on the host instead of once per ray)
+            const float r0 = ro.rgb[0], r1 = ro.rgb[1], r2 = ro.rgb[2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                ro.rgb[i] = fa(fmaf(p.affine[4 * i + 2], r2, fmaf(p.affine[4 * i + 1], r1, fm(p.affine[4 * i], r0))), p.affine[4 * i + 3]);
+        }
         if (p.o_rgb) { p.o_rgb[3 * (size_t)ray] = ro.rgb[0]; p.o_rgb[3 * (size_t)ray + 1] = ro.rgb[1]; p.o_rgb[3 * (size_t)ray + 2] = ro.rgb[2]; }
         if (p.o_depth) p.o_depth[ray] = ro.depth;
         if (p.o_depth_raw) p.o_depth_raw[ray] = ro.depth_raw;

@@ -94,6 +94,8 @@ struct CompositeParams {
     float* weights;          // [N, S]
     // optional per-ray outputs (NULL = skip)
     float *o_rgb, *o_depth, *o_depth_raw, *o_acc, *o_mean, *o_median, *o_p5, *o_p95, *o_packed;
+    int use_affine;          // final level only: rgb <- A rgb + t (BrightnessCorrection, models.py:L339-363)
+    float affine[12];        // row-major [3][4]
 };
 
 int launch_generate_rays(const CameraConst& cam, uint32_t row0, uint32_t n_rows, const RayOutPtrs& o, cudaStream_t st);

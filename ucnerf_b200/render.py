@@ -192,6 +192,16 @@ class HotPathModel:
     def set_option(self, key: str, value: int):
         _lib.check(self.lib.ucnerf_set_option(self._handle, key.encode(), int(value)), "set_option")
 
+    def set_rgb_affine(self, affine):
+        """Brightness-correction affine of the image being rendered ([3,4] or [1,3,4] tensor / array, e.g.
+        `model.brightness_corr(indices=cam_idx)[0]`, extrinsic_optimizer.py:L15-25), applied to the final rgb inside the
+        compositing kernel as models.py:L349 does; None switches it off."""
+        if affine is None:
+            _lib.check(self.lib.ucnerf_set_rgb_affine(self._handle, None), "set_rgb_affine")
+            return
+        a = np.ascontiguousarray(torch.as_tensor(affine).detach().cpu().to(torch.float32).reshape(3, 4).numpy())
+        _lib.check(self.lib.ucnerf_set_rgb_affine(self._handle, a.ctypes.data), "set_rgb_affine")
+
     def timing(self, reset=True):
         """Per kernel family: (device milliseconds, launches) accumulated since the last reset; needs
         set_option("timing", 1)."""
@@ -402,6 +412,16 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
         lrv = torch.randn_like(local['cam_dirs'])
     else:
         lrv = rand_vec[idx] if world > 1 else rand_vec
+    # brightness-correction head (models.py:L339-363): ONE evaluation of the reference module per image, the affine is
+    # applied in the compositing epilogue
+    affine = None
+    if model is not None and getattr(config, "brightness_correction", False):
+        m = model.module if hasattr(model, "module") else model
+        if getattr(config, "model_sky", False):
+            raise NotImplementedError("the sky head (model_sky=True) is outside the fused path")
+        idx_t = torch.as_tensor(eval_camidx).reshape(-1)[:1].to(next(m.brightness_corr.parameters()).device)
+        affine = m.brightness_corr(indices=idx_t.repeat(2))[0]    # .squeeze() in the reference needs >= 2 indices
+    r.set_rgb_affine(affine)
     nl = r.num_levels
     want = ["packed"] + [f"sdist_{l}" for l in range(nl)] + [f"weights_{l}" for l in range(nl)] + ["sample_rgb"]
     out = r.render_rays(local, train_frac, lrv, want)
@@ -437,4 +457,7 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
     rendering["ray_weights"] = [out[f"weights_{l}"][pick] for l in range(nl)]
     rendering["ray_rgbs"] = [final_rgb[:, None, :].expand(-1, r.samples[l], -1) for l in range(nl - 1)] + \
                             [out["sample_rgb"][pick]]
+    if affine is not None:
+        rendering["affine_trans"] = affine[None].expand(num_rays, 3, 4)   # models.py:L361
+        r.set_rgb_affine(None)
     return rendering

@@ -421,7 +421,7 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
             raise NotImplementedError("the sky head (model_sky=True) is outside the fused path")
         idx_t = torch.as_tensor(eval_camidx).reshape(-1)[:1].to(next(m.brightness_corr.parameters()).device)
         affine = m.brightness_corr(indices=idx_t.repeat(2))[0]    # .squeeze() in the reference needs >= 2 indices
-    r.set_rgb_affine(affine)
+        r.set_rgb_affine(affine)    # reset below once the image is rendered
     nl = r.num_levels
     want = ["packed"] + [f"sdist_{l}" for l in range(nl)] + [f"weights_{l}" for l in range(nl)] + ["sample_rgb"]
     out = r.render_rays(local, train_frac, lrv, want)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of colour-MLP experiments (dev tool)
+# colour-MLP experiments (dev tool)
 mkdir -p gpurun_out
 run() {
   name=$1; shift
@@ -8,10 +8,9 @@ run() {
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); k=d['kernel_ms_per_step']
-    print('$name', round(d['ms_per_step'],2), {a:round(b,2) for a,b in k.items()}, d['checksum_mean_rgb'], 'e2e', round(d['e2e']['ms_per_step'],2), 'cam', round(d['e2e_camera']['ms_per_step'],2))
+    print('$name', round(d['ms_per_step'],2), {a:round(b,2) for a,b in k.items()}, d['checksum_mean_rgb'])
 except Exception as e: print('$name', 'FAILED', e)
 "
 }
-run smembias --steps 4 --warmup 3
-run globalbias --steps 4 --warmup 3 --tc-debug 16
-run smembias_1024 --steps 3 --warmup 3 --workload target_1024spp
+run joint --steps 4 --warmup 3
+run joint_1024 --steps 3 --warmup 3 --workload target_1024spp

@@ -249,7 +249,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
     }
     if (threadIdx.x < 4) sR0[threadIdx.x] = p.r0[threadIdx.x];
     if (threadIdx.x == 0) {
-        mbar_init(BAR(A_FULL0), 128); mbar_init(BAR(A_FULL1), 128);
+        mbar_init(BAR(A_FULL0), 256); mbar_init(BAR(A_FULL1), 256);
         mbar_init(BAR(A_EMPTY0), 1); mbar_init(BAR(A_EMPTY1), 1);
         mbar_init(BAR(B_FULL0), 1); mbar_init(BAR(B_FULL1), 1);
         mbar_init(BAR(B_EMPTY0), 1); mbar_init(BAR(B_EMPTY1), 1);
@@ -282,8 +282,6 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         const int g = warp >> 2;                 // warpgroup 0 / 1  == A slot it fills
         const int t = threadIdx.x & 127;         // row inside the tile
         const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        uint8_t* my_slot = smem + kSmemA + g * kASlotBytes;
-        uint32_t k = 0;                          // chunks produced by this group so far (A_EMPTY phase)
         uint32_t it = 0, prev_tile = 0;
         // profiling (debug_flags bit 2): thread 0 of each group in CTA 0 -> dbg[16 + 8 g ...]: total, waits on
         // A_EMPTY / ACC3_FULL / ACC4_FULL+PART, time in h1 chunks / dir chunks / tmem chunks (kilo-cycles)
@@ -359,7 +357,6 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const uint32_t row = tile * kTileM + t;
             const bool valid = row < p.n_rows;
-            const float* h1row = p.h1 + (size_t)(valid ? row : 0) * 64;
             const uint32_t ray = (valid ? row : 0u) / (uint32_t)p.S;
             const float* bias0 = p.dir_bias + (size_t)ray * 512;  // per-ray [c0' | c1'] rows
             if (smem_bias) {
@@ -367,95 +364,94 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                 const uint32_t lr = ray >= f ? min(ray - f, (uint32_t)kBiasRays - 1) : 0u;
                 bias0 = reinterpret_cast<const float*>(sBias + (it & 1) * kBiasStageBytes + lr * 2048);
             }
-#pragma unroll 1
-            for (int c = g; c < kSteps; c += 2) {
+            // ---- chunk H: the h1 tile (128 rows x 64), produced ONCE by all 8 warps and used by steps 0 and 1.
+            // Coalesced: warp w covers rows [16 w, 16 w + 16), one instruction = 2 rows x 256 B (4 lines instead of the
+            // 32 a thread-per-row load touches); lane -> (row parity, 16-byte piece).
+            {
                 const long long tc0 = prof ? clock64() : 0;
+                const uint32_t n = 5u * it, slot = n & 1u, u = n >> 1;
+                const int piece = lane & 15;
+                float4 x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t r = (uint32_t)(16 * warp + 2 * i + (lane >> 4));
+                    const uint32_t grow = tile * kTileM + r;
+                    x[i] = grow < p.n_rows ? __ldg(reinterpret_cast<const float4*>(p.h1 + (size_t)grow * 64) + piece)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                // h1 streams from HBM (1 GB per chunk of rays): pull this CTA's NEXT tile into L2 one tile time ahead
+                if (!(p.debug_flags & 8u)) {
+                    const uint32_t nrow = (tile + gridDim.x) * kTileM + (uint32_t)(threadIdx.x >> 1);
+                    if (nrow < p.n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.h1 + (size_t)nrow * 64 + 32 * (threadIdx.x & 1)));
+                }
+                const long long tb = prof ? clock64() : 0;
+                if (!mbar_wait(BAR(A_EMPTY0 + slot), (u & 1) ^ 1, p.dbg, 2, A_EMPTY0 + slot, it, 0)) goto teardown;
                 long long tw = 0;
-                if (c < 2) {
-                    // the h1 row (64 values): group 0 pairs it with P0 (step 0), group 1 with P1 (step 1)
-                    float4 x[16];
+                if (prof) { tw = clock64() - tb; pw_aempty += tw; }
+                uint8_t* sl = smem + kSmemA + slot * kASlotBytes;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q)
-                        x[q] = valid ? __ldg(reinterpret_cast<const float4*>(h1row) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    // h1 streams from HBM (1 GB per chunk of rays, written by the encode kernel): pull this CTA's NEXT
-                    // tile into L2 now, one whole tile time ahead, so the loads above see L2 instead of DRAM latency
-                    if (g == 0 && !(p.debug_flags & 8u)) {
-                        const uint32_t nrow = (tile + gridDim.x) * kTileM + t;
-                        if (nrow < p.n_rows) {
-                            const float* nx = p.h1 + (size_t)nrow * 64;
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
-                        }
-                    }
-                    const long long tb = prof ? clock64() : 0;
-                    if (!mbar_wait(BAR(A_EMPTY0 + g), (k & 1) ^ 1, p.dbg, 2, A_EMPTY0 + g, it, c)) goto teardown;
-                    if (prof) { tw = clock64() - tb; pw_aempty += tw; }
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        float v[32];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            v[4 * q] = x[8 * hf + q].x * kActScale; v[4 * q + 1] = x[8 * hf + q].y * kActScale;
-                            v[4 * q + 2] = x[8 * hf + q].z * kActScale; v[4 * q + 3] = x[8 * hf + q].w * kActScale;
-                        }
-                        store_a_half(my_slot, t, hf, v);
-                    }
-                } else {
-                    const int j = c - 2;  // columns [64 j, 64 j + 64) of acc3
-                    if (j < 2) {  // first TMEM chunk of this group for this tile
-                        const long long ta = prof ? clock64() : 0;
-                        if (!mbar_wait(BAR(ACC3_FULL), it & 1, p.dbg, 1, ACC3_FULL, it, c)) goto teardown;
-                        if (smem_bias && !mbar_wait(BAR(BIAS_FULL0 + (it & 1)), (it >> 1) & 1, p.dbg, 12, BIAS_FULL0 + (it & 1), it, c)) goto teardown;
-                        if (prof) { tw = clock64() - ta; pw_acc3 += tw; }
-                        tc_fence_after();
-                    }
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32_issue(lane_taddr + (uint32_t)(64 * j), r0);
-                    tmem_ld32_issue(lane_taddr + (uint32_t)(64 * j + 32), r1);
-                    const float4* b0 = reinterpret_cast<const float4*>(bias0 + 64 * j);
-                    float4 bb[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) bb[q] = smem_bias ? b0[q] : __ldg(b0 + q);  // overlaps the TMEM loads
-                    tmem_ld_wait();
-                    if (j >= 2) {  // this group's part of acc3 is in registers
-                        tc_fence_before();
-                        mbar_arrive(BAR(ACC3_EMPTY));
-                    }
-                    const long long tb = prof ? clock64() : 0;
-                    if (!mbar_wait(BAR(A_EMPTY0 + g), (k & 1) ^ 1, p.dbg, 2, A_EMPTY0 + g, it, c)) goto teardown;
-                    if (prof) { const long long d = clock64() - tb; pw_aempty += d; tw += d; }
-                    const float k0 = p.k0;
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        float v[32];
-                        if (hf) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) bb[q] = smem_bias ? b0[8 + q] : __ldg(b0 + 8 + q);
-                        }
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const uint32_t* rr = hf ? r1 : r0;
-                            const float4 bq = bb[q];
-                            v[4 * q] = fmaxf(fmaf(__uint_as_float(rr[4 * q]), k0, bq.x), 0.f);
-                            v[4 * q + 1] = fmaxf(fmaf(__uint_as_float(rr[4 * q + 1]), k0, bq.y), 0.f);
-                            v[4 * q + 2] = fmaxf(fmaf(__uint_as_float(rr[4 * q + 2]), k0, bq.z), 0.f);
-                            v[4 * q + 3] = fmaxf(fmaf(__uint_as_float(rr[4 * q + 3]), k0, bq.w), 0.f);
-                        }
-                        store_a_half(my_slot, t, hf, v);
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 16 * warp + 2 * i + (lane >> 4);
+                    uint2 hi, lo;
+                    split2(x[i].x * kActScale, x[i].y * kActScale, hi.x, lo.x);
+                    split2(x[i].z * kActScale, x[i].w * kActScale, hi.y, lo.y);
+                    // K elements [4 piece, 4 piece + 4): 16-byte unit piece / 2 (swizzled with the row), half piece % 2
+                    uint8_t* dst = sl + (r >> 3) * 1024 + (r & 7) * 128 + (((piece >> 1) ^ (r & 7)) * 16) + (piece & 1) * 8;
+                    *reinterpret_cast<uint2*>(dst) = hi;
+                    *reinterpret_cast<uint2*>(dst + kATileBytes) = lo;
                 }
                 fence_proxy_async();
-                mbar_arrive(BAR(A_FULL0 + g));
-                ++k;
-                if (prof) {
-                    const long long work = clock64() - tc0 - tw;
-                    if (c < 2) pt_h1 += work; else pt_tm += work;
+                mbar_arrive(BAR(A_FULL0 + slot));
+                if (prof) pt_h1 += clock64() - tc0 - tw;
+            }
+            // the previous tile's accumulator drain runs now: the tensor pipe already has this tile's first step
+            if (it > 0) {
+                const long long te = prof ? clock64() : 0;
+                if (!final_epilogue(prev_tile, it - 1)) goto teardown;
+                if (prof) pw_epi += clock64() - te;
+            }
+            // ---- chunks a_j = relu(acc3[:, 64 j : 64 j + 64] k0 + bias0) for steps 2..5: both groups work on every
+            // chunk, group g converts columns [64 j + 32 g, + 32) of its row (half the latency per chunk)
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const long long tc0 = prof ? clock64() : 0;
+                long long tw = 0;
+                const uint32_t n = 5u * it + 1u + (uint32_t)j, slot = n & 1u, u = n >> 1;
+                if (j == 0) {
+                    const long long ta = prof ? clock64() : 0;
+                    if (!mbar_wait(BAR(ACC3_FULL), it & 1, p.dbg, 1, ACC3_FULL, it, j)) goto teardown;
+                    if (smem_bias && !mbar_wait(BAR(BIAS_FULL0 + (it & 1)), (it >> 1) & 1, p.dbg, 12, BIAS_FULL0 + (it & 1), it, j)) goto teardown;
+                    if (prof) { tw = clock64() - ta; pw_acc3 += tw; }
+                    tc_fence_after();
                 }
-                if (c == g && it > 0) {
-                    const long long te = prof ? clock64() : 0;
-                    if (!final_epilogue(prev_tile, it - 1)) goto teardown;
-                    if (prof) pw_epi += clock64() - te;
+                uint32_t r0[32];
+                tmem_ld32_issue(lane_taddr + (uint32_t)(64 * j + 32 * g), r0);
+                const float4* b0 = reinterpret_cast<const float4*>(bias0 + 64 * j + 32 * g);
+                float4 bb[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) bb[q] = smem_bias ? b0[q] : __ldg(b0 + q);  // overlaps the TMEM load
+                tmem_ld_wait();
+                if (j == 3) {  // this thread's last read of acc3
+                    tc_fence_before();
+                    mbar_arrive(BAR(ACC3_EMPTY));
                 }
+                const long long tb = prof ? clock64() : 0;
+                if (!mbar_wait(BAR(A_EMPTY0 + slot), (u & 1) ^ 1, p.dbg, 2, A_EMPTY0 + slot, it, 2 + j)) goto teardown;
+                if (prof) { const long long d = clock64() - tb; pw_aempty += d; tw += d; }
+                const float k0 = p.k0;
+                float v[32];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 bq = bb[q];
+                    v[4 * q] = fmaxf(fmaf(__uint_as_float(r0[4 * q]), k0, bq.x), 0.f);
+                    v[4 * q + 1] = fmaxf(fmaf(__uint_as_float(r0[4 * q + 1]), k0, bq.y), 0.f);
+                    v[4 * q + 2] = fmaxf(fmaf(__uint_as_float(r0[4 * q + 2]), k0, bq.z), 0.f);
+                    v[4 * q + 3] = fmaxf(fmaf(__uint_as_float(r0[4 * q + 3]), k0, bq.w), 0.f);
+                }
+                store_a_half(smem + kSmemA + slot * kASlotBytes, t, g, v);
+                fence_proxy_async();
+                mbar_arrive(BAR(A_FULL0 + slot));
+                if (prof) pt_tm += clock64() - tc0 - tw;
             }
             prev_tile = tile;
         }
@@ -486,10 +482,13 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                     if (prof) { const long long t1 = clock64(); w_acc4 += t1 - t0; t0 = t1; }
                     if (!mbar_wait(BAR(B_FULL0 + slot), phase, p.dbg, 6, B_FULL0 + slot, it, s)) goto teardown;
                     if (prof) { const long long t1 = clock64(); w_b += t1 - t0; t0 = t1; }
-                    if (!mbar_wait(BAR(A_FULL0 + slot), phase, p.dbg, 7, A_FULL0 + slot, it, s)) goto teardown;
+                    // A chunks of a tile: n = 5 it (the h1 tile, steps 0 AND 1), 5 it + 1 .. 5 it + 4 (a_0..a_3, steps 2..5);
+                    // chunk n lives in A slot n & 1 and is its (n >> 1)-th use
+                    const uint32_t an = 5u * it + (s < 2 ? 0u : (uint32_t)(s - 1)), aslot = an & 1u;
+                    if (s != 1 && !mbar_wait(BAR(A_FULL0 + aslot), (an >> 1) & 1, p.dbg, 7, A_FULL0 + aslot, it, s)) goto teardown;
                     if (prof) { const long long t1 = clock64(); w_a += t1 - t0; t0 = t1; }
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + kSmemA + slot * kASlotBytes);
+                    const uint32_t a_hi = smem_u32(smem + kSmemA + aslot * kASlotBytes);
                     const uint32_t a_lo = a_hi + kATileBytes;
                     const uint32_t b_hi = smem_u32(smem + kSmemB + slot * kBSlotBytes);
                     const uint32_t b_lo = b_hi + kBTileBytes;
@@ -503,7 +502,7 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                         umma_f16(acc, dal, dbh, 1u);
                         umma_f16(acc, dah, dbl, 1u);
                     }
-                    umma_commit(BAR(A_EMPTY0 + slot));
+                    if (s != 0) umma_commit(BAR(A_EMPTY0 + aslot));   // the h1 tile is released after step 1
                     umma_commit(BAR(B_EMPTY0 + slot));
                     if (s == 0) umma_commit(BAR(ACC3_FULL));
                     if (s == kSteps - 1) umma_commit(BAR(ACC4_FULL));

@@ -244,8 +244,11 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < 256; i += kThreads) {
-        sR[i] = reinterpret_cast<const float4*>(p.rt)[i];
+    // rgb-layer weights for the packed epilogue: entry 2 q = {x_k, x_k+1, y_k, y_k+1}, 2 q + 1 = {z_k, z_k+1, 0, 0}, k = 2 q
+    for (int i = threadIdx.x; i < 128; i += kThreads) {
+        const float4 w0 = reinterpret_cast<const float4*>(p.rt)[2 * i], w1 = reinterpret_cast<const float4*>(p.rt)[2 * i + 1];
+        sR[2 * i] = make_float4(w0.x, w1.x, w0.y, w1.y);
+        sR[2 * i + 1] = make_float4(w0.z, w1.z, 0.f, 0.f);
     }
     if (threadIdx.x < 4) sR0[threadIdx.x] = p.r0[threadIdx.x];
     if (threadIdx.x == 0) {
@@ -293,8 +296,9 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
         auto final_epilogue = [&](uint32_t tl, uint32_t itp) -> bool {
             if (!mbar_wait(BAR(ACC4_FULL), itp & 1, p.dbg, 3, ACC4_FULL, itp, 99)) return false;
             tc_fence_after();
-            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-            const float k1 = p.k1;
+            // packed fp32x2 math: two neighbouring columns per FFMA2 (even / odd partial sums of the three outputs)
+            float2 o0 = make_float2(0.f, 0.f), o1 = make_float2(0.f, 0.f), o2 = make_float2(0.f, 0.f);
+            const float2 k1 = make_float2(p.k1, p.k1);
             const uint32_t erow = tl * kTileM + t;
             const uint32_t eray = (erow < p.n_rows ? erow : 0u) / (uint32_t)p.S;
             const float4* bias1;
@@ -317,27 +321,35 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                 tmem_ld_wait();
                 uint32_t (&cur)[32] = (jj & 1) ? rb : ra;
                 uint32_t (&nxt)[32] = (jj & 1) ? ra : rb;
-                if (jj < 3) tmem_ld32_issue(lane_taddr + (uint32_t)(256 + g * 128 + 32 * (jj + 1)), nxt);
-                const int col = g * 128 + 32 * jj;
+                if (jj < 3) {
+                    tmem_ld32_issue(lane_taddr + (uint32_t)(256 + g * 128 + 32 * (jj + 1)), nxt);
+                } else {
+                    // every TMEM read of this thread has completed: hand acc4 back before the last block's arithmetic
+                    tc_fence_before();
+                    mbar_arrive(BAR(ACC4_EMPTY));
+                }
+                const int pair0 = (g * 128 + 32 * jj) / 2;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float bq[4] = {bb[q].x, bb[q].y, bb[q].z, bb[q].w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float a2 = fmaxf(fmaf(__uint_as_float(cur[4 * q + e]), k1, bq[e]), 0.f);
-                        const float4 w = sR[col + 4 * q + e];
-                        o0 = fmaf(a2, w.x, o0);
-                        o1 = fmaf(a2, w.y, o1);
-                        o2 = fmaf(a2, w.z, o2);
-                    }
+                    float2 a01 = ffma2(make_float2(__uint_as_float(cur[4 * q]), __uint_as_float(cur[4 * q + 1])), k1, make_float2(bb[q].x, bb[q].y));
+                    float2 a23 = ffma2(make_float2(__uint_as_float(cur[4 * q + 2]), __uint_as_float(cur[4 * q + 3])), k1, make_float2(bb[q].z, bb[q].w));
+                    a01.x = fmaxf(a01.x, 0.f); a01.y = fmaxf(a01.y, 0.f);
+                    a23.x = fmaxf(a23.x, 0.f); a23.y = fmaxf(a23.y, 0.f);
+                    const float4 wa = sR[2 * (pair0 + 2 * q)], wb = sR[2 * (pair0 + 2 * q) + 1];
+                    const float4 wc = sR[2 * (pair0 + 2 * q + 1)], wd = sR[2 * (pair0 + 2 * q + 1) + 1];
+                    o0 = ffma2(a01, make_float2(wa.x, wa.y), o0);
+                    o1 = ffma2(a01, make_float2(wa.z, wa.w), o1);
+                    o2 = ffma2(a01, make_float2(wb.x, wb.y), o2);
+                    o0 = ffma2(a23, make_float2(wc.x, wc.y), o0);
+                    o1 = ffma2(a23, make_float2(wc.z, wc.w), o1);
+                    o2 = ffma2(a23, make_float2(wd.x, wd.y), o2);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(BAR(ACC4_EMPTY));
+            const float s0 = o0.x + o0.y, s1 = o1.x + o1.y, s2 = o2.x + o2.y;
             if (smem_bias) mbar_arrive(BAR(BIAS_EMPTY0 + (itp & 1)));   // last read of this tile's staged biases
             if (g == 1) {
                 if (!mbar_wait(BAR(PART_EMPTY), (itp & 1) ^ 1, p.dbg, 9, PART_EMPTY, itp, 99)) return false;
-                sPart[t] = make_float4(o0, o1, o2, 0.f);
+                sPart[t] = make_float4(s0, s1, s2, 0.f);
                 mbar_arrive(BAR(PART_FULL));
             } else {
                 if (!mbar_wait(BAR(PART_FULL), itp & 1, p.dbg, 10, PART_FULL, itp, 99)) return false;
@@ -346,9 +358,9 @@ color_mlp_tc_kernel(const __grid_constant__ ColorTcParams p) {
                 const uint32_t row = tl * kTileM + t;
                 if (row < p.n_rows) {
                     float* o = p.rgb + (size_t)row * 3;
-                    o[0] = fs(fm(sigmoid_f(o0 + q.x + sR0[0]), p.rgb_scale), p.rgb_padding);
-                    o[1] = fs(fm(sigmoid_f(o1 + q.y + sR0[1]), p.rgb_scale), p.rgb_padding);
-                    o[2] = fs(fm(sigmoid_f(o2 + q.z + sR0[2]), p.rgb_scale), p.rgb_padding);
+                    o[0] = fs(fm(sigmoid_f(s0 + q.x + sR0[0]), p.rgb_scale), p.rgb_padding);
+                    o[1] = fs(fm(sigmoid_f(s1 + q.y + sR0[1]), p.rgb_scale), p.rgb_padding);
+                    o[2] = fs(fm(sigmoid_f(s2 + q.z + sR0[2]), p.rgb_scale), p.rgb_padding);
                 }
             }
             return true;

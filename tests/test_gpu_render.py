@@ -318,3 +318,24 @@ def test_resample_kernel_matches_cpu_instantiation_on_concentrated_histogram(har
     got = out.cpu().numpy()
     assert np.abs(got - ref).max() < 2e-6
     assert np.all(np.diff(got, axis=1) >= 0)
+
+
+@pytest.mark.parametrize("s_nerf", [33, 48, 160])
+def test_tensor_core_path_with_sample_counts_that_do_not_tile(s_nerf):
+    """NeRF-level sample counts that are not a multiple of 32: a 128-row tile of the tensor-core colour MLP then
+    spans up to five rays (staged per-ray bias rows) and rays straddle tiles; against the oracle."""
+    cfg = O.waymo_config()
+    cfg.num_nerf_samples = s_nerf
+    params = O.init_params(cfg, seed=4)
+    batch = O.synthetic_rays(77, seed=12)
+    r = build_renderer(cfg, params)
+    r.set_option("color_mlp", 1)
+    out = run(r, batch)
+    rend, hist = O.model_forward(params, cfg, batch)
+    for k in ("rgb", "acc", "depth_raw"):
+        err = np.abs(out[k] - rend[-1][k].numpy()).max()
+        assert err < TOL, (s_nerf, k, err)
+    assert np.abs(out["sample_rgb"] - hist[-1]["rgb"].numpy()).max() < 5e-4
+    r.set_option("color_mlp", 0)
+    simt = run(r, batch)
+    assert np.abs(simt["rgb"] - out["rgb"]).max() < 2e-5

@@ -30,3 +30,31 @@ def param_checksums(params):
     import torch
     return {k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in params.items()
             if v.dtype == torch.float32}
+
+
+def make_heads(seed=0, n_views=9):
+    """Seeded weights of the sky head (`skynerf.*`, models.py:L84-92,L743-795) and the brightness-correction head
+    (`brightness_corr.*`, extrinsic_optimizer.py:L4-39) under the reference state_dict names, nn.Linear-style init."""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+
+    def linear(name, fin, fout, scale=1.0):
+        b = scale / math.sqrt(fin)
+        out[name + '.weight'] = (torch.rand((fout, fin), generator=g) * 2 - 1) * b
+        out[name + '.bias'] = (torch.rand((fout,), generator=g) * 2 - 1) * b
+
+    for i in range(8):
+        linear(f'skynerf.pts_linears.{i}', 3 if i == 0 else (259 if i == 5 else 256), 256, 1.7)
+    linear('skynerf.views_linears.0', 283, 128, 1.7)
+    linear('skynerf.feature_linear', 256, 256)
+    linear('skynerf.alpha_linear', 256, 1, 8.0)
+    linear('skynerf.rgb_linear', 128, 3, 4.0)
+    out['brightness_corr.latent_code'] = torch.randn((n_views, 4), generator=g) * 0.5
+    out['brightness_corr.sky_latent_code'] = torch.randn((n_views, 4), generator=g) * 0.5
+    linear('brightness_corr.brightness_MLP.pts_linears.0', 4, 256)
+    linear('brightness_corr.brightness_MLP.pts_linears.1', 256, 256)
+    linear('brightness_corr.brightness_MLP.pts_linears.2', 256, 256)
+    linear('brightness_corr.brightness_MLP.output_linear', 256, 12, 4.0)
+    return out

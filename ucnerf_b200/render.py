@@ -388,7 +388,9 @@ def _get_renderer(model, config):
 @torch.no_grad()
 def render_image(model, accelerator, batch, rand, train_frac, config, verbose=True, return_weights=False,
                  eval_camidx=0, rand_vec=None, renderer: Optional[HotPathModel] = None):
-    """Drop-in for internal/models.py:L907-1007 `render_image` (fused forward path, heads excluded).
+    """Drop-in for internal/models.py:L907-1007 `render_image`: fused forward path; with `config.brightness_correction`
+    the affine is applied in the compositing kernel, with `config.model_sky` the reference's own sky head runs on top
+    (keys `sky_rgbs`, `affine_trans`, `affine_trans_sky` as models.py:L336-363).
 
     model: a reference `Model` (a HotPathModel is built from it once and cached on the module) or None when
     `renderer` is given.  accelerator: only process_index / num_processes are read."""
@@ -412,25 +414,37 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
         lrv = torch.randn_like(local['cam_dirs'])
     else:
         lrv = rand_vec[idx] if world > 1 else rand_vec
-    # brightness-correction head (models.py:L339-363): ONE evaluation of the reference module per image, the affine is
-    # applied in the compositing epilogue
-    affine = None
-    if model is not None and getattr(config, "brightness_correction", False):
-        m = model.module if hasattr(model, "module") else model
-        if getattr(config, "model_sky", False):
-            raise NotImplementedError("the sky head (model_sky=True) is outside the fused path")
+    # heads of the shipped Waymo configuration (scripts/train_waymo.sh: model_sky + brightness_correction).
+    # Brightness (models.py:L339-363): ONE evaluation of the reference module per image, the affine is applied in the
+    # compositing epilogue.  Sky (models.py:L326-337): the reference's own `render_rays` + `skynerf` run unchanged on
+    # this rank's tile ("run unchanged on top"); its tensor-core kernel is §8f N1.
+    affine = affine_sky = None
+    m = (model.module if hasattr(model, "module") else model) if model is not None else None
+    use_sky = m is not None and getattr(config, "model_sky", False)
+    if m is not None and getattr(config, "brightness_correction", False):
         idx_t = torch.as_tensor(eval_camidx).reshape(-1)[:1].to(next(m.brightness_corr.parameters()).device)
-        affine = m.brightness_corr(indices=idx_t.repeat(2))[0]    # .squeeze() in the reference needs >= 2 indices
+        res = m.brightness_corr(indices=idx_t.repeat(2))          # .squeeze() in the reference needs >= 2 indices
+        affine, affine_sky = (res[0][0], res[1][0]) if use_sky else (res[0], None)
         r.set_rgb_affine(affine)    # reset below once the image is rendered
     nl = r.num_levels
     want = ["packed"] + [f"sdist_{l}" for l in range(nl)] + [f"weights_{l}" for l in range(nl)] + ["sample_rgb"]
     out = r.render_rays(local, train_frac, lrv, want)
     packed = out["packed"]
+    sky_rgbs = None
+    if use_sky:
+        sky_rgbs = _reference_sky_head(m, local, getattr(config, "render_chunk_size", 16384))
+        if affine_sky is not None:  # models.py:L353-354
+            sky_opacity = 1 - torch.sum(out[f"weights_{nl - 1}"], dim=-1, keepdim=True)
+            packed[:, 0:3] += sky_opacity * (sky_rgbs @ affine_sky[:3, :3].T + affine_sky[:3, 3])
     if world > 1:
         import torch.distributed as dist
         full = torch.empty((world * per, PACKED_WIDTH), device=r.device, dtype=torch.float32)
         dist.all_gather_into_tensor(full, packed)  # the ONE collective per image
         packed = full[:num_rays]
+        if sky_rgbs is not None:
+            fs_ = torch.empty((world * per, 3), device=r.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(fs_, sky_rgbs.contiguous())
+            sky_rgbs = fs_[:num_rays]
     rendering = {
         "rgb": packed[:, 0:3].reshape(height, width, 3),
         "depth": packed[:, 3].reshape(height, width),
@@ -457,7 +471,26 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
     rendering["ray_weights"] = [out[f"weights_{l}"][pick] for l in range(nl)]
     rendering["ray_rgbs"] = [final_rgb[:, None, :].expand(-1, r.samples[l], -1) for l in range(nl - 1)] + \
                             [out["sample_rgb"][pick]]
+    if sky_rgbs is not None:
+        rendering["sky_rgbs"] = sky_rgbs.reshape(height, width, 3)       # models.py:L336-337
     if affine is not None:
-        rendering["affine_trans"] = affine[None].expand(num_rays, 3, 4)   # models.py:L361
+        rendering["affine_trans"] = affine[None].expand(num_rays, 3, 4)   # models.py:L361-363
+        if affine_sky is not None:
+            rendering["affine_trans_sky"] = affine_sky[None].expand(num_rays, 3, 4)
         r.set_rgb_affine(None)
     return rendering
+
+
+def _reference_sky_head(m, rays, chunk):
+    """models.py:L326-337 on a flat ray dict: the reference's `render_rays(ray_batch, network_fn=model.skynerf)`
+    (resolved from the module the live model class comes from), chunked so the 120-sample activations fit."""
+    import sys
+    render_rays = getattr(sys.modules[type(m).__module__], "render_rays")
+    o, d, far, cam = rays["origins"], rays["directions"], rays["far"].reshape(-1, 1), rays["cam_dirs"]
+    outs = []
+    for a in range(0, o.shape[0], chunk):
+        sky_near = far[a:a + chunk]
+        sky_far = torch.full_like(sky_near * 1.2, float(far[0]) * 1.5)   # L329: the first ray's far for the whole batch
+        ray_batch = torch.concat([o[a:a + chunk], d[a:a + chunk], sky_near, sky_far, cam[a:a + chunk]], dim=-1)
+        outs.append(render_rays(ray_batch=ray_batch, network_fn=m.skynerf)["rgb_map"])
+    return torch.cat(outs)

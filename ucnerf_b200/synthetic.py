@@ -49,6 +49,8 @@ class Workload:
 WORKLOADS = {
     # BASELINE.json configs[1] as SURVEY.md section 8(d) restates it: one 800x600 eval frame, waymo.gin shapes
     "eval_800x600_waymo_gin": Workload("eval_800x600_waymo_gin"),
+    # BASELINE.json configs[2]/[3] image size: one full-resolution Waymo frame (datasets.py:L896-897), hot path only
+    "eval_1920x1280_waymo_gin": Workload("eval_1920x1280_waymo_gin", height=1280, width=1920),
     # north_star "1024 samples/ray synthetic rays": 512 prop + 512 fine, 65,536 rays (256x256)
     "target_1024spp": Workload("target_1024spp", num_prop_samples=512, num_nerf_samples=512, height=256, width=256),
     # BASELINE.json configs[0]: the reference's CPU-runnable case

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Secondary benchmark (not the driver contract): the tensor-core sky head (ucnerf_sky_render)
+against the same head evaluated the reference's way - PyTorch fp32 Linear layers (cuBLAS SGEMM, TF32 off) over
+120 samples per ray, chunked like render_image does - on one 800x600 frame of synthetic rays.  One JSON line.
+
+    python bench_sky.py [--rays 480000] [--reps 3]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import torch
+
+from oracle import cases, ucnerf_oracle as O          # weights + the torch restatement used as the "reference way" arm
+from ucnerf_b200 import synthetic
+from ucnerf_b200.render import SkyHead
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, default=480000)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--torch-rays", type=int, default=60000, help="rays of the PyTorch arm (scaled to the full frame)")
+    a = ap.parse_args()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    heads = cases.make_heads(seed=3)
+    head = SkyHead(heads)
+    rays = synthetic.pinhole_rays(600, 800, seed=0)
+    n = min(a.rays, rays["origins"].shape[0])
+    o, d, far, cam = (rays[k][:n].cuda() for k in ("origins", "directions", "far", "cam_dirs"))
+
+    def timeit(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms = timeit(lambda: head.render(o, d, far, cam), a.reps)
+    hp = {k: v.cuda() for k, v in heads.items()}
+    nt = min(a.torch_rays, n)
+
+    def torch_arm():
+        with torch.no_grad():
+            for s in range(0, nt, 15000):
+                O.sky_render_rays(hp, o[s:s + 15000], d[s:s + 15000], far[s:s + 15000], cam[s:s + 15000])
+
+    try:
+        torch.set_default_device("cuda")
+        ms_t = timeit(torch_arm, 1) * n / nt
+    finally:
+        torch.set_default_device("cpu")
+    flops = 2.0 * 562688 * n * 120
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    print(json.dumps({"bench": "sky_head", "rays": n, "samples_per_ray": 120, "ms": ms, "rays_per_sec": n / ms * 1e3,
+                      "algorithmic_tflops": flops / ms / 1e9, "tensor_roofline_frac": flops / ms / 1e9 / peak,
+                      "tensor_peak_tflops": peak, "issued_tflops_3term_fp16_split": 3 * flops / ms / 1e9,
+                      "pytorch_fp32_ms": ms_t, "speedup_vs_pytorch_fp32": ms_t / ms,
+                      "note": "PyTorch arm = the same MLP as fp32 nn.Linear layers (cuBLAS SGEMM, TF32 off), timed on "
+                              f"{nt} rays and scaled to {n}"}))
+
+
+if __name__ == "__main__":
+    main()

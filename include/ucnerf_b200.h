@@ -216,6 +216,34 @@ int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value);
  * off.  The sky branch of that code (model_sky=True) is not part of the fused path. */
 int ucnerf_set_rgb_affine(ucnerf_model* m, const float* affine12_host);
 
+/* ---- sky head on tensor cores ----
+ * Replaces models.py:L326-337: ray_batch = [origins, directions, near = far, far = 1.5 far[0], cam_dirs] ->
+ * render_rays(network_fn = skynerf) -> rgb_map (models.py:L743-904: NeRF D=8 W=256 raw-xyz input, skip after layer 4,
+ * 4-frequency view embedding; 120 samples; raw2outputs), bug-compatible with the reference's sample depths
+ * z = near (1 - t) + (1 / far) t.  Weight pointers are DEVICE pointers to the reference state_dict tensors
+ * (nn.Linear layout [out, in]); they are copied / re-laid-out at creation. */
+typedef struct ucnerf_sky_desc {
+    const float* pts_w[8];   /* skynerf.pts_linears.{0..7}.weight  [256,3] [256,256]x4 [256,259] [256,256]x2 */
+    const float* pts_b[8];   /* skynerf.pts_linears.{0..7}.bias    [256] */
+    const float* feature_w;  /* skynerf.feature_linear.weight [256,256] */
+    const float* feature_b;
+    const float* alpha_w;    /* skynerf.alpha_linear.weight [1,256] */
+    const float* alpha_b;
+    const float* views_w;    /* skynerf.views_linears.0.weight [128,283] */
+    const float* views_b;
+    const float* rgb_w;      /* skynerf.rgb_linear.weight [3,128] */
+    const float* rgb_b;
+    int32_t n_samples;       /* render_rays N_samples (120) */
+} ucnerf_sky_desc;
+
+typedef struct ucnerf_sky ucnerf_sky;  /* opaque */
+int ucnerf_sky_create(const ucnerf_sky_desc* desc, ucnerf_sky** out);
+int ucnerf_sky_destroy(ucnerf_sky* sky);
+/* origins, directions, views (= the batch's cam_dirs) [N,3], far [N] device arrays; sky_far = 1.5 * far[0] as the
+ * reference computes it on the host (models.py:L329); sky_rgb [N,3] device output = ret['rgb_map']. */
+int ucnerf_sky_render(ucnerf_sky* sky, uint64_t n_rays, const float* origins, const float* directions, const float* far,
+                      const float* views, double sky_far, float* sky_rgb, void* stream);
+
 /* Timing probe: with option "timing" != 0, ucnerf_render_rays records a CUDA event pair around every kernel
  * launch on the launch stream (no synchronisation is added).  ucnerf_get_timing waits for the recorded events
  * and returns accumulated device milliseconds and launch counts per kernel family:

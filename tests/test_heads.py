@@ -42,13 +42,20 @@ def render_rays(ray_batch, network_fn, N_samples=120, **_):
 
 
 class _Sky(torch.nn.Module):
+    """Stand-in with the reference NeRF's parameter names (models.py:L785-795), so its state_dict feeds SkyHead."""
+
     def __init__(self, heads):
         super().__init__()
-        self.p = {k: v.cuda() for k, v in heads.items()}
+        L = torch.nn.Linear
+        self.pts_linears = torch.nn.ModuleList([L(3, 256)] + [L(259 if i == 4 else 256, 256) for i in range(7)])
+        self.views_linears = torch.nn.ModuleList([L(283, 128)])
+        self.feature_linear, self.alpha_linear, self.rgb_linear = L(256, 256), L(256, 1), L(128, 3)
+        self.load_state_dict({k[len("skynerf."):]: v for k, v in heads.items() if k.startswith("skynerf.")})
+        self.cuda()
 
     def forward(self, pts, views):
         import oracle.ucnerf_oracle as OO
-        return OO.sky_nerf_forward(self.p, pts, views)
+        return OO.sky_nerf_forward({"skynerf." + k: v for k, v in self.state_dict().items()}, pts, views)
 
 
 class _Brightness(torch.nn.Module):
@@ -91,6 +98,12 @@ def test_gpu_render_image_with_sky_and_brightness_heads():
     conf = types.SimpleNamespace(model_sky=True, brightness_correction=True, render_chunk_size=20, vis_num_rays=4)
     img = R.render_image(model, None, b2d, False, 1.0, conf, renderer=r, eval_camidx=torch.tensor(int(g["cam"])),
                          rand_vec=b2d["rand_vec"].reshape(-1, 3))
+    assert isinstance(model._ucnerf_b200_sky, R.SkyHead)          # the tensor-core sky kernel was used
+    conf_ref = types.SimpleNamespace(model_sky=True, brightness_correction=True, render_chunk_size=20, vis_num_rays=4,
+                                     ucnerf_reference_sky=True)  # same image through the reference-module head
+    img_ref = R.render_image(model, None, b2d, False, 1.0, conf_ref, renderer=r, eval_camidx=torch.tensor(int(g["cam"])),
+                             rand_vec=b2d["rand_vec"].reshape(-1, 3))
+    assert (img_ref["rgb"] - img["rgb"]).abs().max().item() < 1e-4
     sky = img["sky_rgbs"].reshape(n, 3).cpu().numpy()
     assert np.abs(sky - g["sky_rgbs"]).max() < 2e-5 * max(1.0, np.abs(g["sky_rgbs"]).max())
     assert np.abs(img["affine_trans"][0].cpu().numpy() - g["affine"]).max() < 1e-6
@@ -106,3 +119,28 @@ def test_gpu_render_image_with_sky_and_brightness_heads():
     img2 = R.render_image(model, None, b2d, False, 1.0, conf2, renderer=r, rand_vec=b2d["rand_vec"].reshape(-1, 3))
     assert torch.equal(img2["rgb"], plain["rgb"]) and "affine_trans" not in img2
     assert np.abs(img2["sky_rgbs"].reshape(n, 3).cpu().numpy() - g["sky_rgbs"]).max() < 2e-5 * max(1.0, np.abs(g["sky_rgbs"]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_rays", [48, 1000])
+def test_gpu_sky_head_tensor_core_kernel_matches_oracle(n_rays):
+    """ucnerf_sky_render (tcgen05 8x256 MLP + per-ray integration) against the oracle restatement that is pinned
+    bit-for-bit to the reference's render_rays / NeRF.forward / raw2outputs."""
+    from ucnerf_b200.render import SkyHead
+    heads = cases.make_heads(seed=3, n_views=9)
+    head = SkyHead(heads)
+    batch = O.synthetic_rays(n_rays, seed=5)
+    got = head.render(batch["origins"].cuda(), batch["directions"].cuda(), batch["far"].cuda(), batch["cam_dirs"].cuda())
+    torch.cuda.synchronize()
+    st = (__import__("ctypes").c_uint32 * 32)()
+    head.lib.ucnerf_debug_sky_status(st)
+    assert st[0] == 0, list(st)[:8]
+    want = O.sky_render_rays(heads, batch["origins"], batch["directions"], batch["far"], batch["cam_dirs"])
+    err = (got.cpu() - want).abs().max().item()
+    scale = max(1.0, want.abs().max().item())
+    assert err < 1e-4 * scale, (err, scale)
+    if n_rays == 48:   # the golden vectors come from the reference itself
+        g = load_golden("heads")
+        cfg, params, b48 = cases.make_case("waymo", 48)
+        got48 = head.render(b48["origins"].cuda(), b48["directions"].cuda(), b48["far"].cuda(), b48["cam_dirs"].cuda())
+        assert np.abs(got48.cpu().numpy() - g["sky_rgbs"]).max() < 1e-4 * max(1.0, np.abs(g["sky_rgbs"]).max())

@@ -85,13 +85,19 @@ class RayBuffers(C.Structure):
                 ("origins", "directions", "viewdirs", "cam_dirs", "radii", "near", "far", "rand_vec", "imageplane")]
 
 
+class SkyDesc(C.Structure):
+    _fields_ = [("pts_w", C.c_void_p * 8), ("pts_b", C.c_void_p * 8), ("feature_w", C.c_void_p), ("feature_b", C.c_void_p),
+                ("alpha_w", C.c_void_p), ("alpha_b", C.c_void_p), ("views_w", C.c_void_p), ("views_b", C.c_void_p),
+                ("rgb_w", C.c_void_p), ("rgb_b", C.c_void_p), ("n_samples", C.c_int32)]
+
+
 # every symbol include/ucnerf_b200.h declares (tests/test_abi_symbols.py checks the .so exports them)
 EXPORTS = [
     "ucnerf_abi_version", "ucnerf_last_error", "ucnerf_grid_encode_forward", "ucnerf_grid_encode_backward",
     "ucnerf_grad_total_variation", "ucnerf_model_create", "ucnerf_model_refresh", "ucnerf_model_destroy",
     "ucnerf_render_rays", "ucnerf_render_rays_host", "ucnerf_launch_count", "ucnerf_set_option",
     "ucnerf_get_timing", "ucnerf_generate_rays", "ucnerf_render_camera", "ucnerf_render_camera_host",
-    "ucnerf_set_rgb_affine",
+    "ucnerf_set_rgb_affine", "ucnerf_sky_create", "ucnerf_sky_destroy", "ucnerf_sky_render",
 ]
 
 _lib = None
@@ -130,6 +136,9 @@ def load():
     lib.ucnerf_render_camera.argtypes = [vp, C.POINTER(Camera), u32, u32, C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_render_camera_host.argtypes = [vp, C.POINTER(Camera), u32, u32, C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_set_rgb_affine.argtypes = [vp, vp]
+    lib.ucnerf_sky_create.argtypes = [C.POINTER(SkyDesc), C.POINTER(vp)]
+    lib.ucnerf_sky_destroy.argtypes = [vp]
+    lib.ucnerf_sky_render.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_double, vp, vp]
     lib.ucnerf_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.ucnerf_get_timing.argtypes = [vp, c_float_p, C.POINTER(C.c_uint32), C.c_int]
     lib.ucnerf_debug_u_grid.argtypes = [C.c_int, vp]

@@ -81,6 +81,25 @@ struct ColorTcParams {
     uint32_t debug_flags;    // profiling experiments only (ucnerf_set_option "tc_debug"); 0 in production
 };
 
+// sky head (sky_mlp_tc.cu): 8x256 NeRF MLP at n_samples depths per ray, tensor cores
+struct SkyTcParams {
+    uint32_t n_rows;          // n_rays * n_samples
+    int n_samples;
+    const float *origins, *directions, *far;   // per ray
+    const float* t_vals;      // [n_samples] torch.linspace(0, 1, n_samples)
+    float sky_far;            // 1.5 x far[0] (models.py:L329)
+    const float* view_bias;   // [n_rays][128]: b_v + W_v[:, 256:283] emb(view)
+    const uint8_t* wblob;     // 38 weight chunks (hi | lo FP16, UMMA K-major SWIZZLE_128B), 64 KB stride
+    const float* bias8;       // [9][256]: biases of layers 0..7 and the feature layer, x activation scale
+    float k[10];              // accumulator -> value factors per layer
+    const float* w_alpha;     // [256]
+    float b_alpha;
+    const float* rgb_w;       // [128][4]
+    float rgb_b[3];
+    float* raw;               // [n_rows][4] = rgb_raw, alpha_raw
+    uint32_t* dbg;
+};
+
 struct CompositeParams {
     uint32_t n_rays;
     int S;
@@ -111,6 +130,14 @@ int launch_dir_bias(const float* viewdirs, const float* wdir, const float* c0, c
 void color_tc_pack_chunk(const float* wt_rows, float scale, uint8_t* dst);
 float color_tc_weight_scale(const float* w, size_t n);
 float color_tc_act_scale();
+int launch_sky_mlp_tc(const SkyTcParams& p, cudaStream_t st);
+int launch_sky_view_bias(const float* views, const float* wv_view, const float* bv, float* out, uint32_t n_rays, cudaStream_t st);
+int launch_sky_composite(const float* raw, const float* directions, const float* far, const float* t_vals, float sky_far,
+                         int n_samples, float* out, uint32_t n_rays, cudaStream_t st);
+int sky_tc_status(uint32_t* out32);
+uint32_t sky_tc_blob_bytes();
+float sky_tc_act_scale();
+void sky_tc_pack_chunk(const float* wt_rows, int n_cols, float scale, uint8_t* dst);
 int sample_encode_lmax(int L);
 // h1 column c holds hidden unit kH1Perm(c) of density_layer.0 (layout written by sample_encode_kernel)
 inline int h1_perm(int c) { return (c / 16) + 4 * (c % 16); }  // padded level count used by the kernel instantiation (0 = unsupported)

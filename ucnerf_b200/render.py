@@ -367,6 +367,69 @@ class HotPathModel:
         return renderings, history
 
 
+class SkyHead:
+    """Tensor-core sky head (ucnerf_sky_*): the reference's `render_rays(ray_batch, network_fn=model.skynerf)`
+    (internal/models.py:L326-337, L743-904) for the architecture `Model` builds (D=8, W=256, raw-xyz input, skip after
+    layer 4, 4-frequency view embedding, 120 samples).  Built from a state_dict with the reference key names
+    (`skynerf.pts_linears.N.weight` ...)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], prefix: str = "skynerf", n_samples: int = 120, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.UcnerfError("ucnerf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        g = lambda k: state_dict[f"{prefix}.{k}"].detach().to(self.device, torch.float32).contiguous()
+        shapes = {"pts_linears.0.weight": (256, 3), "pts_linears.5.weight": (256, 259), "views_linears.0.weight": (128, 283),
+                  "feature_linear.weight": (256, 256), "alpha_linear.weight": (1, 256), "rgb_linear.weight": (3, 128)}
+        for k, shp in shapes.items():
+            if tuple(state_dict[f"{prefix}.{k}"].shape) != shp:
+                raise NotImplementedError(f"sky head: {prefix}.{k} has shape {tuple(state_dict[f'{prefix}.{k}'].shape)}, "
+                                          f"the tensor-core kernel implements the reference architecture {shp}")
+        d = _lib.SkyDesc()
+        keep = []
+        for i in range(8):
+            w, b = g(f"pts_linears.{i}.weight"), g(f"pts_linears.{i}.bias")
+            keep += [w, b]
+            d.pts_w[i], d.pts_b[i] = w.data_ptr(), b.data_ptr()
+        for name, fw, fb in (("feature_linear", "feature_w", "feature_b"), ("alpha_linear", "alpha_w", "alpha_b"),
+                             ("views_linears.0", "views_w", "views_b"), ("rgb_linear", "rgb_w", "rgb_b")):
+            w, b = g(name + ".weight"), g(name + ".bias")
+            keep += [w, b]
+            setattr(d, fw, w.data_ptr())
+            setattr(d, fb, b.data_ptr())
+        d.n_samples = n_samples
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            _lib.check(self.lib.ucnerf_sky_create(C.byref(d), C.byref(self._handle)), "sky_create")
+        del keep
+
+    def render(self, origins, directions, far, views) -> torch.Tensor:
+        """[N,3] origins / directions / views (= the batch's cam_dirs), far [N] or [N,1] -> sky rgb_map [N,3]."""
+        n = origins.shape[0]
+        t = [x.detach().to(self.device, torch.float32).contiguous() for x in (origins, directions, far.reshape(-1), views)]
+        out = torch.empty((n, 3), device=self.device, dtype=torch.float32)
+        if n == 0:
+            return out
+        sky_far = float(t[2][0]) * 1.5        # models.py:L329 (the same host read the reference does)
+        with torch.cuda.device(self.device):
+            rc = self.lib.ucnerf_sky_render(self._handle, n, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(),
+                                            sky_far, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "sky_render")
+        return out
+
+    def close(self):
+        if self._handle:
+            self.lib.ucnerf_sky_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def shard_bounds(num_rays: int, world: int, rank: int):
     """Contiguous tile [start, stop) of rank `rank`; every rank renders ceil(num_rays / world) rays (the last
     tiles are padded by re-rendering the final ray) so one fixed-size all-gather moves the image."""
@@ -432,7 +495,7 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
     packed = out["packed"]
     sky_rgbs = None
     if use_sky:
-        sky_rgbs = _reference_sky_head(m, local, getattr(config, "render_chunk_size", 16384))
+        sky_rgbs = _sky_head(m, local, config)
         if affine_sky is not None:  # models.py:L353-354
             sky_opacity = 1 - torch.sum(out[f"weights_{nl - 1}"], dim=-1, keepdim=True)
             packed[:, 0:3] += sky_opacity * (sky_rgbs @ affine_sky[:3, :3].T + affine_sky[:3, 3])
@@ -479,6 +542,23 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
             rendering["affine_trans_sky"] = affine_sky[None].expand(num_rays, 3, 4)
         r.set_rgb_affine(None)
     return rendering
+
+
+def _sky_head(m, rays, config):
+    """Sky colours of a flat ray dict: the tensor-core kernel when `model.skynerf` has the reference architecture (a
+    SkyHead is built once and cached on the module), else - or with `config.ucnerf_reference_sky = True` - the
+    reference's own torch head."""
+    if not getattr(config, "ucnerf_reference_sky", False):
+        head = getattr(m, "_ucnerf_b200_sky", None)
+        if head is None:
+            try:
+                head = SkyHead({"skynerf." + k: v for k, v in m.skynerf.state_dict().items()}, device=rays["origins"].device)
+            except (NotImplementedError, KeyError):
+                head = False
+            object.__setattr__(m, "_ucnerf_b200_sky", head)
+        if head:
+            return head.render(rays["origins"], rays["directions"], rays["far"], rays["cam_dirs"])
+    return _reference_sky_head(m, rays, getattr(config, "render_chunk_size", 16384))
 
 
 def _reference_sky_head(m, rays, chunk):

@@ -154,15 +154,19 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
             tc_fence_after();
             const float k = p.k[layer];
             const float* bias = sBias + layer * 256;
-#pragma unroll 1
+            // software pipeline over the four chunks: the TMEM load of chunk j + 1 is in flight while chunk j is converted
+            uint32_t ra[32], rb[32];
+            tmem_ld32_issue(lane_taddr + (uint32_t)(256 * acc + 32 * g), ra);
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
-                uint32_t r0[32];
-                tmem_ld32_issue(lane_taddr + (uint32_t)(256 * acc + 64 * j + 32 * g), r0);
+                uint32_t (&r0)[32] = (j & 1) ? rb : ra;
+                uint32_t (&rn)[32] = (j & 1) ? ra : rb;
                 const float4* b0 = reinterpret_cast<const float4*>(bias + 64 * j + 32 * g);
                 float4 bb[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) bb[q] = b0[q];
                 tmem_ld_wait();
+                if (j < 3) tmem_ld32_issue(lane_taddr + (uint32_t)(256 * acc + 64 * (j + 1) + 32 * g), rn);
                 if (!wait_slot(n_first + (uint32_t)j, (uint32_t)(10 * layer + j))) return false;
                 float v[32];
 #pragma unroll

@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--encode-runs", type=int, default=-1, help="A/B: cell-run reuse in the encode kernel (bit0 prop, bit1 NeRF); -1 = library default")
+    ap.add_argument("--heads", action="store_true", help="also time the frame with the sky + brightness heads of the "
+                    "shipped Waymo configuration (BASELINE.json configs[2]); reported under `with_heads`")
     ap.add_argument("--tc-debug", type=int, default=0, help="profiling experiment flags for the TC kernel (invalid results)")
     return ap.parse_args()
 
@@ -251,6 +253,42 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_cam = float(t.item())
+    # ---- optional: the frame with the heads of scripts/train_waymo.sh (sky head kernel + brightness affine) --------
+    heads_info = None
+    if args.heads:
+        from ucnerf_b200.render import SkyHead
+        hsd = synthetic.synthetic_heads(seed=0)
+        sky = SkyHead(hsd, device=dev)
+        aff_sky = hsd["affine_sky"].to(dev)
+
+        def step_heads():
+            r.set_rgb_affine(hsd["affine"])
+            out = r.render_rays(rays_d, 1.0, rays_d["rand_vec"], ("packed", f"weights_{r.num_levels - 1}"))
+            srgb = sky.render(rays_d["origins"], rays_d["directions"], rays_d["far"], rays_d["cam_dirs"])
+            opac = 1 - out[f"weights_{r.num_levels - 1}"].sum(-1, keepdim=True)      # models.py:L351-354
+            out["packed"][:, 0:3] += opac * (srgb @ aff_sky[:3, :3].T + aff_sky[:3, 3])
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out["packed"])
+            return out
+
+        for _ in range(2):
+            step_heads()
+        sync_all()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        for _ in range(args.steps):
+            step_heads()
+        e5.record()
+        sync_all()
+        r.set_rgb_affine(None)
+        t = torch.tensor([e4.elapsed_time(e5)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_h = float(t.item()) / args.steps
+        heads_info = {"ms_per_step": ms_h, "rays_per_sec": world * n / (ms_h * 1e-3),
+                      "sky_head_ms": ms_h - ms / args.steps, "sky_samples_per_ray": 120,
+                      "note": "fused foreground path + tensor-core sky head (8x256 MLP x 120 samples per ray) + both "
+                              "brightness affines, models.py:L326-363; device-resident rays"}
     clocks = sampler.stop() if sampler else None
     checksum = float(out_h["packed"][:, :3].double().mean())
 
@@ -319,6 +357,8 @@ def main():
                                        "bytes_per_ray": wl.gather_bytes_per_ray()},
             "clocks": clocks, "checksum_mean_rgb": checksum,
         }
+        if heads_info:
+            line["with_heads"] = heads_info
         if world == 1 and not args.no_cpu_baseline:
             ns = args.cpu_sample_rays or (128 if wl.num_prop_samples >= 512 else 8192)
             v, dt, ns = time_cpu_port(wl, sd, rays_h, ns)

@@ -153,6 +153,29 @@ def pinhole_rays(height, width, seed=0, near=0.0, far=8.0, focal=None) -> Dict[s
                 rand_vec=torch.randn((n, 3), generator=g))
 
 
+def synthetic_heads(seed=0, n_views=9) -> Dict[str, torch.Tensor]:
+    """Random-init weights of the sky head (`skynerf.*`, internal/models.py:L84-92,L743-795) and of the brightness
+    affines of one camera, under the reference state_dict names (nn.Linear-style init), on CPU."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def linear(name, fin, fout):
+        b = 1.0 / math.sqrt(fin)
+        sd[name + '.weight'] = (torch.rand((fout, fin), generator=g) * 2 - 1) * b
+        sd[name + '.bias'] = (torch.rand((fout,), generator=g) * 2 - 1) * b
+
+    for i in range(8):
+        linear(f'skynerf.pts_linears.{i}', 3 if i == 0 else (259 if i == 5 else 256), 256)
+    linear('skynerf.views_linears.0', 283, 128)
+    linear('skynerf.feature_linear', 256, 256)
+    linear('skynerf.alpha_linear', 256, 1)
+    linear('skynerf.rgb_linear', 128, 3)
+    eye = torch.cat([torch.eye(3), torch.zeros(3, 1)], 1)
+    sd['affine'] = eye + 0.05 * torch.randn((3, 4), generator=g)
+    sd['affine_sky'] = eye + 0.05 * torch.randn((3, 4), generator=g)
+    return sd
+
+
 def make_renderer(wl: Workload, state_dict, device=None):
     from .render import HotPathModel
     dev = device or f"cuda:{torch.cuda.current_device()}"

@@ -38,6 +38,34 @@ class FakeRenderer:
         return {k: out[k] for k in want}
 
 
+def render_rays(ray_batch, network_fn, **_):
+    """Stand-in for the reference's module-level render_rays (models.py:L849-904): any per-ray function will do here."""
+    return {"rgb_map": network_fn(ray_batch[:, 0:3], ray_batch[:, 3:6]) + ray_batch[:, 6:7]}
+
+
+class _Sky(torch.nn.Module):
+    def forward(self, o, d):
+        return torch.sin(o * 3.0) + 0.5 * d
+
+
+class _Bright(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, indices):
+        n = indices.reshape(-1).shape[0]
+        a = torch.tensor([[1.1, 0.0, 0.1, 0.01], [0.0, 0.9, 0.0, -0.02], [0.05, 0.0, 1.0, 0.0]])
+        b = torch.tensor([[0.8, 0.1, 0.0, 0.03], [0.0, 1.2, 0.0, 0.0], [0.0, 0.0, 0.7, 0.05]])
+        return a.expand(n, 3, 4), b.expand(n, 3, 4)
+
+
+class HeadsModel(torch.nn.Module):   # `render_rays` above is resolved through this class's module
+    def __init__(self):
+        super().__init__()
+        self.skynerf, self.brightness_corr = _Sky(), _Bright()
+
+
 class Acc:
     def __init__(self):
         self.process_index = dist.get_rank()
@@ -68,6 +96,37 @@ def main():
         assert torch.equal(img["distance_percentile_95"], origins[..., 1] + 8)
         assert img["weights"].shape == (H, W, 4) and torch.equal(img["weights"][..., 0], origins[..., 0])
         assert len(img["ray_sdist"]) == 2 and img["ray_rgbs"][0].shape == (4, 8, 3)
+        # heads of the shipped config on top (sky through the reference-module path, brightness affines): the sharded
+        # result must equal the single-process one
+        class HCfg(Cfg):
+            model_sky, brightness_correction, ucnerf_reference_sky = True, True, True
+
+        class FakeAffine(FakeRenderer):
+            affine = None
+
+            def set_rgb_affine(self, a):
+                FakeAffine.affine = a
+
+            def render_rays(self, batch, train_frac, rand_vec, want):
+                out = super().render_rays(batch, train_frac, rand_vec, want)
+                if FakeAffine.affine is not None:
+                    a = FakeAffine.affine
+                    out["packed"][:, 0:3] = out["packed"][:, 0:3] @ a[:3, :3].T + a[:3, 3]
+                return out
+
+        hm = HeadsModel()
+        img_h = R.render_image(hm, Acc(), batch, False, 1.0, HCfg(), renderer=FakeAffine(), eval_camidx=torch.tensor(2),
+                               rand_vec=torch.zeros(H * W, 3))
+
+        class One:
+            process_index, num_processes, is_main_process = 0, 1, True
+
+        ref_h = R.render_image(hm, One(), batch, False, 1.0, HCfg(), renderer=FakeAffine(), eval_camidx=torch.tensor(2),
+                               rand_vec=torch.zeros(H * W, 3))
+        for k in ("rgb", "sky_rgbs", "acc", "depth"):
+            assert torch.allclose(img_h[k], ref_h[k], atol=1e-6), k
+        assert img_h["sky_rgbs"].shape == (H, W, 3) and img_h["affine_trans_sky"].shape == (H * W, 3, 4)
+        assert not torch.allclose(img_h["rgb"], img["rgb"])
     else:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         sys.path.insert(0, os.path.join(ROOT, "tests"))

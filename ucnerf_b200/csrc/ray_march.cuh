@@ -88,10 +88,10 @@ struct SkyTcParams {
     const float *origins, *directions, *far;   // per ray
     const float* t_vals;      // [n_samples] torch.linspace(0, 1, n_samples)
     float sky_far;            // 1.5 x far[0] (models.py:L329)
-    const float* view_bias;   // [n_rays][128]: b_v + W_v[:, 256:283] emb(view)
-    const uint8_t* wblob;     // 38 weight chunks (hi | lo FP16, UMMA K-major SWIZZLE_128B), 64 KB stride
-    const float* bias8;       // [9][256]: biases of layers 0..7 and the feature layer, x activation scale
-    float k[10];              // accumulator -> value factors per layer
+    const float* view_bias;   // [n_rays][128]: b_v + W_vf b_f + W_v[:, 256:283] emb(view)
+    const uint8_t* wblob;     // 34 weight chunks (hi | lo FP16, UMMA K-major SWIZZLE_128B), 64 KB stride
+    const float* bias8;       // [8][256]: biases of layers 0..7, x activation scale
+    float k[10];              // accumulator -> value factors: layers 0..7, [8] = folded view layer
     const float* w_alpha;     // [256]
     float b_alpha;
     const float* rgb_w;       // [128][4]
@@ -136,6 +136,7 @@ int launch_sky_composite(const float* raw, const float* directions, const float*
                          int n_samples, float* out, uint32_t n_rays, cudaStream_t st);
 int sky_tc_status(uint32_t* out32);
 uint32_t sky_tc_blob_bytes();
+int sky_tc_steps();
 float sky_tc_act_scale();
 void sky_tc_pack_chunk(const float* wt_rows, int n_cols, float scale, uint8_t* dst);
 int sample_encode_lmax(int L);

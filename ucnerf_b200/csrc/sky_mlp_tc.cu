@@ -5,19 +5,21 @@
 //   h0 = relu(W0 p + b0)                  p = o + d z (raw xyz, K = 3)
 //   h_l = relu(W_l h_{l-1} + b_l)         l = 1..7, 256 wide; layer 5 takes [p, h4] (skip connection, K = 259)
 //   alpha = w_a . h7 + b_a                (CUDA cores, folded into the conversion of h7)
-//   f = W_f h7 + b_f                      (no activation)
-//   v = relu(W_v [f, emb(view)] + b_v)    128 wide; the view part is a per-ray bias (sky_view_bias_kernel)
+//   f = W_f h7 + b_f                      (no activation)            } folded on the host (fp64): v = relu(W' h7 + b'(ray)),
+//   v = relu(W_v [f, emb(view)] + b_v)    128 wide                   } W' = W_vf W_f, b' = b_v + W_vf b_f + W_vv emb(view)
 //   rgb = W_r v + b_r                     (CUDA cores in the epilogue)
 //
 // Same machinery as color_mlp_tc.cu (tc_common.cuh): 128-row tiles, persistent CTAs, two producer / epilogue
 // warpgroups + one MMA issuer + one weight loader, tcgen05.mma kind::f16 with fp32 accumulators in TMEM, every operand
 // as an FP16 hi + lo pair (3-term split: fp32-level accuracy), weights pre-scaled / pre-split / pre-swizzled on the
-// host and streamed L2 -> smem with cp.async.bulk.  38 K-chunks (= MMA steps = weight chunks) per tile:
-//   step 0        p      x W0          -> acc0            steps 17..21  [p, h4] x W5   -> acc1
-//   steps 1..4    h0     x W1          -> acc1            steps 22..25  h5 x W6        -> acc0
-//   steps 5..8    h1     x W2          -> acc0            steps 26..29  h6 x W7        -> acc1
-//   steps 9..12   h2     x W3          -> acc1            steps 30..33  h7 x Wf        -> acc0
-//   steps 13..16  h3     x W4          -> acc0            steps 34..37  f  x Wv (N=128)-> acc1
+// host and streamed L2 -> smem with cp.async.bulk.  34 K-chunks (= MMA steps = weight chunks) per tile:
+//   step 0        p      x W0          -> layer 0         steps 17..21  [p, h4] x W5   -> layer 5
+//   steps 1..4    h0     x W1          -> layer 1         steps 22..25  h5 x W6        -> layer 6
+//   steps 5..8    h1     x W2          -> layer 2         steps 26..29  h6 x W7        -> layer 7
+//   steps 9..12   h2     x W3          -> layer 3         steps 30..33  h7 x W' (N=128)-> layer 8 (view layer)
+//   steps 13..16  h3     x W4          -> layer 4
+// Layer l of the it-th tile of a CTA accumulates into TMEM accumulator (l + it) & 1 (nine layers per tile, so the
+// accumulator the view layer of one tile is drained from is not the one layer 0 of the next tile writes).
 // The two TMEM accumulators (256 columns each) ping-pong: while layer l accumulates into one, both warpgroups drain
 // the other (tcgen05.ld -> scale + bias -> relu -> FP16 split -> swizzled smem) chunk by chunk into the A ring that
 // feeds layer l.  The per-sample outputs (rgb_raw, alpha_raw) go to HBM; sky_composite_kernel integrates them per ray
@@ -43,8 +45,9 @@ constexpr uint32_t kSmemB = kSmemA + 2 * kASlotBytes;            // 65536
 constexpr uint32_t kSmemMisc = kSmemB + 2 * kBSlotBytes;         // 196608
 constexpr uint32_t kOffBar = 0;
 constexpr uint32_t kOffTmem = 192;
-constexpr uint32_t kOffBias = 256;                                // [9][256] floats (already x kActScale)
-constexpr uint32_t kOffWa = kOffBias + 9 * 1024;                  // [256] alpha weights
+constexpr int kStepsPerTile = 34;
+constexpr uint32_t kOffBias = 256;                                // [8][256] floats (already x kActScale)
+constexpr uint32_t kOffWa = kOffBias + 8 * 1024;                  // [256] alpha weights
 constexpr uint32_t kOffRgbW = kOffWa + 1024;                      // [128] float4 (rgb weights, w = 0)
 constexpr uint32_t kOffPart = kOffRgbW + 2048;                    // [128] float4 partial sums group 1 -> group 0
 constexpr uint32_t kMiscBytes = kOffPart + 2048;
@@ -55,7 +58,7 @@ constexpr int kMmaWarp = 8;
 constexpr uint32_t kIdesc256 = make_idesc(256), kIdesc128 = make_idesc(128);
 
 enum Bar { A_FULL0 = 0, A_FULL1, A_EMPTY0, A_EMPTY1, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, ACC_FULL0, ACC_FULL1,
-           ACC1_EMPTY, PART_FULL, PART_EMPTY, NUM_BARS };
+           EPI_DONE, PART_FULL, PART_EMPTY, NUM_BARS };
 static_assert(NUM_BARS * 8 <= kOffTmem, "barrier block overlaps the TMEM pointer slot");
 
 }  // namespace sky
@@ -76,7 +79,7 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
     float4* sPart = reinterpret_cast<float4*>(misc + kOffPart);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 9 * 256; i += kThreads) sBias[i] = p.bias8[i];
+    for (int i = threadIdx.x; i < 8 * 256; i += kThreads) sBias[i] = p.bias8[i];
     for (int i = threadIdx.x; i < 256; i += kThreads) sWa[i] = p.w_alpha[i];
     for (int i = threadIdx.x; i < 128; i += kThreads) sRgbW[i] = reinterpret_cast<const float4*>(p.rgb_w)[i];
     if (threadIdx.x == 0) {
@@ -85,7 +88,7 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
         mbar_init(BAR(B_FULL0), 1); mbar_init(BAR(B_FULL1), 1);
         mbar_init(BAR(B_EMPTY0), 1); mbar_init(BAR(B_EMPTY1), 1);
         mbar_init(BAR(ACC_FULL0), 1); mbar_init(BAR(ACC_FULL1), 1);
-        mbar_init(BAR(ACC1_EMPTY), 256);
+        mbar_init(BAR(EPI_DONE), 256);
         mbar_init(BAR(PART_FULL), 128); mbar_init(BAR(PART_EMPTY), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -109,6 +112,9 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
         const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t it = 0, prev_tile = 0;
         float alpha_part = 0.f, alpha_prev = 0.f;
+        uint32_t use[2] = {0u, 0u};          // completed fills of each accumulator this thread has consumed
+        int epi_acc = 0;
+        uint32_t epi_use = 0;                // accumulator / fill index of the previous tile's view layer
 
         // A chunk n of the running sequence lives in slot n & 1 and is its (n >> 1)-th use
         auto wait_slot = [&](uint32_t n, uint32_t step) -> bool {
@@ -149,9 +155,12 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
             return true;
         };
         // drain one accumulator into four A chunks: v = act(acc k + bias8[col]); thread = (row t, 32 columns of each chunk)
-        auto convert = [&](int acc, uint32_t acc_use, int layer, bool relu, bool with_alpha, uint32_t n_first) -> bool {
-            if (!mbar_wait(BAR(ACC_FULL0 + acc), acc_use & 1u, p.dbg, 1, ACC_FULL0 + acc, it, (uint32_t)layer)) return false;
+        auto convert = [&](int layer, bool with_alpha, uint32_t n_first) -> bool {
+            const int acc = (layer + (int)it) & 1;
+            if (!mbar_wait(BAR(ACC_FULL0 + acc), use[acc] & 1u, p.dbg, 1, ACC_FULL0 + acc, it, (uint32_t)layer)) return false;
+            use[acc] += 1;
             tc_fence_after();
+            constexpr bool relu = true;
             const float k = p.k[layer];
             const float* bias = sBias + layer * 256;
             // software pipeline over the four chunks: the TMEM load of chunk j + 1 is in flight while chunk j is converted
@@ -192,19 +201,19 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
         };
         // drain the view layer (acc1, 128 columns) of tile `tl`, rgb layer, hand the raw outputs out
         auto final_epilogue = [&](uint32_t tl, uint32_t itp) -> bool {
-            if (!mbar_wait(BAR(ACC_FULL1), (5u * itp + 4u) & 1u, p.dbg, 3, ACC_FULL1, itp, 99)) return false;
+            if (!mbar_wait(BAR(ACC_FULL0 + epi_acc), epi_use & 1u, p.dbg, 3, ACC_FULL0 + epi_acc, itp, 99)) return false;
             tc_fence_after();
             uint32_t ra[32], rb[32];
-            tmem_ld32_issue(lane_taddr + (uint32_t)(256 + 64 * g), ra);
-            tmem_ld32_issue(lane_taddr + (uint32_t)(256 + 64 * g + 32), rb);
+            tmem_ld32_issue(lane_taddr + (uint32_t)(256 * epi_acc + 64 * g), ra);
+            tmem_ld32_issue(lane_taddr + (uint32_t)(256 * epi_acc + 64 * g + 32), rb);
             const uint32_t row = tl * kTileM + t;
             const uint32_t ray = (row < p.n_rows ? row : 0u) / (uint32_t)p.n_samples;
             const float4* vb = reinterpret_cast<const float4*>(p.view_bias + (size_t)ray * 128 + 64 * g);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(BAR(ACC1_EMPTY));
+            mbar_arrive(BAR(EPI_DONE));
             float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-            const float k9 = p.k[9];
+            const float k9 = p.k[8];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const float4 b = __ldg(vb + q);
@@ -237,23 +246,25 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
         };
 
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const uint32_t n0 = 38u * it;
+            const uint32_t n0 = (uint32_t)kStepsPerTile * it;
             if (!produce_p(tile, n0)) goto teardown;
             if (it > 0) {
                 if (!final_epilogue(prev_tile, it - 1)) goto teardown;
             }
-            if (!convert(0, 5u * it + 0u, 0, true, false, n0 + 1)) goto teardown;    // h0 -> layer 1
-            if (!convert(1, 5u * it + 0u, 1, true, false, n0 + 5)) goto teardown;    // h1 -> layer 2
-            if (!convert(0, 5u * it + 1u, 2, true, false, n0 + 9)) goto teardown;    // h2 -> layer 3
-            if (!convert(1, 5u * it + 1u, 3, true, false, n0 + 13)) goto teardown;   // h3 -> layer 4
-            if (!produce_p(tile, n0 + 17)) goto teardown;                             // xyz again: skip connection
-            if (!convert(0, 5u * it + 2u, 4, true, false, n0 + 18)) goto teardown;   // h4 -> layer 5
-            if (!convert(1, 5u * it + 2u, 5, true, false, n0 + 22)) goto teardown;   // h5 -> layer 6
-            if (!convert(0, 5u * it + 3u, 6, true, false, n0 + 26)) goto teardown;   // h6 -> layer 7
+            if (!convert(0, false, n0 + 1)) goto teardown;    // h0 -> layer 1
+            if (!convert(1, false, n0 + 5)) goto teardown;    // h1 -> layer 2
+            if (!convert(2, false, n0 + 9)) goto teardown;    // h2 -> layer 3
+            if (!convert(3, false, n0 + 13)) goto teardown;   // h3 -> layer 4
+            if (!produce_p(tile, n0 + 17)) goto teardown;     // xyz again: skip connection
+            if (!convert(4, false, n0 + 18)) goto teardown;   // h4 -> layer 5
+            if (!convert(5, false, n0 + 22)) goto teardown;   // h5 -> layer 6
+            if (!convert(6, false, n0 + 26)) goto teardown;   // h6 -> layer 7
             alpha_part = 0.f;
-            if (!convert(1, 5u * it + 3u, 7, true, true, n0 + 30)) goto teardown;    // h7 -> feature layer (+ alpha)
+            if (!convert(7, true, n0 + 30)) goto teardown;    // h7 -> view layer (+ alpha)
             alpha_prev = alpha_part;
-            if (!convert(0, 5u * it + 4u, 8, false, false, n0 + 34)) goto teardown;  // feature -> view layer
+            epi_acc = (8 + (int)it) & 1;                      // the view layer's accumulator, drained during the next tile
+            epi_use = use[epi_acc];
+            use[epi_acc] += 1;
             prev_tile = tile;
         }
         if (it > 0) {
@@ -265,26 +276,27 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
             uint32_t it = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
 #pragma unroll 1
-                for (int s = 0; s < 38; ++s) {
+                for (int s = 0; s < kStepsPerTile; ++s) {
                     // layer of this step, whether it opens / closes the layer, and its accumulator
                     int layer, first, last;
                     if (s == 0) { layer = 0; first = 1; last = 1; }
                     else if (s <= 16) { layer = 1 + (s - 1) / 4; first = ((s - 1) & 3) == 0; last = ((s - 1) & 3) == 3; }
                     else if (s <= 21) { layer = 5; first = s == 17; last = s == 21; }
                     else { layer = 6 + (s - 22) / 4; first = ((s - 22) & 3) == 0; last = ((s - 22) & 3) == 3; }
-                    const uint32_t acc_i = (uint32_t)(layer & 1);
+                    const uint32_t acc_i = (uint32_t)((layer + (int)it) & 1);
                     const bool p_step = (s == 0 || s == 17);
-                    if (s == 1 && !mbar_wait(BAR(ACC1_EMPTY), (it & 1) ^ 1, p.dbg, 5, ACC1_EMPTY, it, s)) goto teardown;
-                    const uint32_t m = 38u * it + (uint32_t)s, slot = m & 1u, ph = (m >> 1) & 1u;
+                    // layer 1 writes the accumulator the previous tile's view layer is drained from
+                    if (s == 1 && !mbar_wait(BAR(EPI_DONE), (it & 1) ^ 1, p.dbg, 5, EPI_DONE, it, s)) goto teardown;
+                    const uint32_t m = (uint32_t)kStepsPerTile * it + (uint32_t)s, slot = m & 1u, ph = (m >> 1) & 1u;
                     if (!mbar_wait(BAR(B_FULL0 + slot), ph, p.dbg, 6, B_FULL0 + slot, it, s)) goto teardown;
                     if (!mbar_wait(BAR(A_FULL0 + slot), ph, p.dbg, 7, A_FULL0 + slot, it, s)) goto teardown;
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + kSmemA + slot * kASlotBytes);
                     const uint32_t a_lo = a_hi + kATileBytes;
                     const uint32_t b_hi = smem_u32(smem + kSmemB + slot * kBSlotBytes);
-                    const uint32_t b_lo = b_hi + (layer == 9 ? kBTileBytes / 2 : kBTileBytes);
+                    const uint32_t b_lo = b_hi + (layer == 8 ? kBTileBytes / 2 : kBTileBytes);
                     const uint32_t acc = tmem_base + 256u * acc_i;
-                    const uint32_t idesc = layer == 9 ? kIdesc128 : kIdesc256;
+                    const uint32_t idesc = layer == 8 ? kIdesc128 : kIdesc256;
                     const int nks = p_step ? 1 : kKC / 16;
                     for (int ks = 0; ks < nks; ++ks) {
                         const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
@@ -305,10 +317,10 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
             uint32_t it = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
 #pragma unroll 1
-                for (int s = 0; s < 38; ++s) {
-                    const uint32_t m = 38u * it + (uint32_t)s, slot = m & 1u, ph = (m >> 1) & 1u;
+                for (int s = 0; s < kStepsPerTile; ++s) {
+                    const uint32_t m = (uint32_t)kStepsPerTile * it + (uint32_t)s, slot = m & 1u, ph = (m >> 1) & 1u;
                     if (!mbar_wait(BAR(B_EMPTY0 + slot), ph ^ 1u, p.dbg, 8, B_EMPTY0 + slot, it, s)) goto teardown;
-                    const uint32_t bytes = s >= 34 ? kBSlotBytes / 2 : kBSlotBytes;
+                    const uint32_t bytes = s >= 30 ? kBSlotBytes / 2 : kBSlotBytes;
                     mbar_expect_tx(BAR(B_FULL0 + slot), bytes);
                     bulk_g2s(smem_u32(smem + kSmemB + slot * kBSlotBytes), p.wblob + (size_t)s * kBSlotBytes, bytes,
                              BAR(B_FULL0 + slot));
@@ -437,7 +449,8 @@ int launch_sky_composite(const float* raw, const float* directions, const float*
     return 0;
 }
 
-uint32_t sky_tc_blob_bytes() { return 38u * kBSlotBytes; }
+uint32_t sky_tc_blob_bytes() { return (uint32_t)kStepsPerTile * kBSlotBytes; }
+int sky_tc_steps() { return kStepsPerTile; }
 float sky_tc_act_scale() { return kActScale; }
 
 // Host: one K-major [64][n_cols] fp32 block -> hi tile | lo tile of (w * scale) in the UMMA K-major SWIZZLE_128B image

@@ -97,18 +97,27 @@ extern "C" int ucnerf_sky_create(const ucnerf_sky_desc* d, ucnerf_sky** out) {
     if (int e = sky_fetch(Bv, d->views_b, 128)) return fail(e);
     if (int e = sky_fetch(Wr, d->rgb_w, 3 * 128)) return fail(e);
     if (int e = sky_fetch(Br, d->rgb_b, 3)) return fail(e);
-    // ---- 38 weight chunks in step order (sky_mlp_tc.cu header) ----
+    // ---- fold the activation-free feature layer into the view layer (fp64): W' = W_vf W_f, b' = b_v + W_vf b_f ----
+    std::vector<float> wfold((size_t)128 * 256), bfold(128);
+    for (int n = 0; n < 128; ++n) {
+        double bacc = Bv[n];
+        for (int j = 0; j < 256; ++j) bacc += (double)Wv[(size_t)n * 283 + j] * (double)Bf[j];
+        bfold[n] = (float)bacc;
+        for (int k = 0; k < 256; ++k) {
+            double acc = 0.0;
+            for (int j = 0; j < 256; ++j) acc += (double)Wv[(size_t)n * 283 + j] * (double)Wf[(size_t)j * 256 + k];
+            wfold[(size_t)n * 256 + k] = (float)acc;
+        }
+    }
+    // ---- 34 weight chunks in step order (sky_mlp_tc.cu header) ----
+    const int nsteps = sky_tc_steps();
     std::vector<uint8_t> blob(sky_tc_blob_bytes(), 0);
-    const size_t stride = blob.size() / 38;
+    const size_t stride = blob.size() / nsteps;
     std::vector<float> wt((size_t)64 * 256);
     int step = 0;
-    float sw[10];
-    std::vector<float> wv_feat((size_t)128 * 256);
-    for (int n = 0; n < 128; ++n)
-        for (int k = 0; k < 256; ++k) wv_feat[(size_t)n * 256 + k] = Wv[(size_t)n * 283 + k];
+    float sw[9];
     for (int l = 0; l < 8; ++l) sw[l] = pow2_scale(W[l]);
-    sw[8] = pow2_scale(Wf);
-    sw[9] = pow2_scale(wv_feat);
+    sw[8] = pow2_scale(wfold);
     auto pack_block = [&](const std::vector<float>& w, int fin, int col0, int kcount, int n_cols, float scale) {
         // Wt[k][n] = w[n][col0 + k] for k < kcount, zero beyond
         std::fill(wt.begin(), wt.end(), 0.f);
@@ -124,15 +133,14 @@ extern "C" int ucnerf_sky_create(const ucnerf_sky_desc* d, ucnerf_sky** out) {
     for (int j = 0; j < 4; ++j) pack_block(W[5], 259, 3 + 64 * j, 64, 256, sw[5]);  // steps 18..21
     for (int l = 6; l <= 7; ++l)
         for (int j = 0; j < 4; ++j) pack_block(W[l], 256, 64 * j, 64, 256, sw[l]);  // steps 22..29
-    for (int j = 0; j < 4; ++j) pack_block(Wf, 256, 64 * j, 64, 256, sw[8]);        // steps 30..33
-    for (int j = 0; j < 4; ++j) pack_block(wv_feat, 256, 64 * j, 64, 128, sw[9]);   // steps 34..37 (N = 128)
-    if (step != 38) { set_error("sky_create: internal chunk count"); return fail(1); }
-    for (int l = 0; l < 9; ++l) s->k[l] = 1.f / sw[l];
-    s->k[9] = 1.f / (act * sw[9]);
-    std::vector<float> bias8((size_t)9 * 256);
+    for (int j = 0; j < 4; ++j) pack_block(wfold, 256, 64 * j, 64, 128, sw[8]);     // steps 30..33: folded view layer (N = 128)
+    if (step != nsteps) { set_error("sky_create: internal chunk count"); return fail(1); }
+    for (int l = 0; l < 8; ++l) s->k[l] = 1.f / sw[l];
+    s->k[8] = 1.f / (act * sw[8]);
+    s->k[9] = 0.f;
+    std::vector<float> bias8((size_t)8 * 256);
     for (int l = 0; l < 8; ++l)
         for (int c = 0; c < 256; ++c) bias8[(size_t)l * 256 + c] = B[l][c] * act;
-    for (int c = 0; c < 256; ++c) bias8[(size_t)8 * 256 + c] = Bf[c] * act;
     std::vector<float> rgbw((size_t)128 * 4, 0.f), wvv((size_t)27 * 128);
     for (int k = 0; k < 128; ++k)
         for (int c = 0; c < 3; ++c) rgbw[(size_t)k * 4 + c] = Wr[(size_t)c * 128 + k];
@@ -152,7 +160,7 @@ extern "C" int ucnerf_sky_create(const ucnerf_sky_desc* d, ucnerf_sky** out) {
     if (int e = sky_upload(s->w_alpha, Wa.data(), 256 * 4)) return fail(e);
     if (int e = sky_upload(s->rgb_w, rgbw.data(), rgbw.size() * 4)) return fail(e);
     if (int e = sky_upload(s->wv_view, wvv.data(), wvv.size() * 4)) return fail(e);
-    if (int e = sky_upload(s->bv, Bv.data(), 128 * 4)) return fail(e);
+    if (int e = sky_upload(s->bv, bfold.data(), 128 * 4)) return fail(e);
     if (int e = sky_upload(s->t_vals, tv.data(), tv.size() * 4)) return fail(e);
     *out = s;
     return 0;

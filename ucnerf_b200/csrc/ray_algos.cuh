@@ -13,6 +13,7 @@
 // position is ~5e-4 of a cell; keeping these chains bit-identical removes that error source.
 #pragma once
 #include <math.h>
+#include <string.h>
 #include <stdint.h>
 #include "common.cuh"
 
@@ -156,6 +157,24 @@ struct ShiftedLeq {
     const float* a; float off, v;
     UC_HD bool operator()(int i) const { return fa(a[i], off) <= v; }
 };
+// first index >= start where the predicate is false (ties / short runs: the caller knows pred holds before `start`)
+template <class Pred>
+UC_HD int advance_while(int n, int start, const Pred pred) {
+    int i = start;
+    while (i < n && pred(i)) ++i;
+    return i;
+}
+UC_HD float bits_to_float(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+UC_HD uint32_t float_to_bits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+
 template <class Pred>
 UC_HD int partition_from(int n, int guess, const Pred pred) {
     if (n <= 0) return 0;
@@ -202,9 +221,12 @@ struct ResampleScratch {
     float* W;   // [3n+1]
     float* CW;  // [3n+2] (>= nb+1) ; also [>= 2] for level 0
     float* C;   // [S]
+    float* J;   // [3n+1] packed (jhi << 16 | jlo) bin ranges of the dilation, as raw bits; aliases W: entry k is read
+                // by the lane that then writes W[k]
     UC_HD static size_t floats(int n, int S) { return (size_t)(n + 1) + n + 2 * (3 * n + 1) + (3 * n + 2) + S; }
     UC_HD void carve(float* base, int n, int S) {
         tp = base; pp = tp + (n + 1); T = pp + n; W = T + (3 * n + 1); CW = W + (3 * n + 1); C = CW + (3 * n + 2);
+        J = W;
         (void)S;
     }
 };
@@ -236,35 +258,56 @@ UC_HD void resample_ray(const X& ex, int n, const float* t_prev, const float* w_
         const float* tp = sc.tp;
         // stepfun.py:L77-80: sort(cat[t, t-d, t+d]) then clip to the domain [0,1]; a 3-way merge of
         // three sorted lists done by ranking (ties ordered A<B<C, values equal so order is moot)
+        // The same searches also give, for every merged fencepost T, the contiguous range of dilated bins that cover it
+        // (stepfun.py:L81-87: t0_j <= T < t1_j  <=>  j in [jlo, jhi), jhi = #{j : t0_j <= T}, jlo = #{j : t1_j <= T}):
+        // the strict counts are extended over ties, fenceposts clipped to the domain ends fall back to a search.
         for (int k = lane; k < m; k += st) {
             float v;
-            int rank;
-            if (k <= n) {  // A: t
+            int rank, jhi, jlo;
+            if (k <= n) {  // A: t  (always inside [0,1]: T = v)
                 v = tp[k];
-                rank = k + partition_from(n, k, ShiftedLess{tp, -dilation, v});            // #B < v
-                rank += partition_from(n, k - 2, ShiftedLess{tp + 1, dilation, v});        // #C < v
-            } else if (k < 2 * n + 1) {  // B: t[:-1] - d
+                const int nb = partition_from(n, k, ShiftedLess{tp, -dilation, v});            // #B < v
+                const int nc = partition_from(n, k - 2, ShiftedLess{tp + 1, dilation, v});     // #C < v
+                rank = k + nb + nc;
+                jhi = advance_while(n, nb, ShiftedLeq{tp, -dilation, v});
+                jlo = advance_while(n, nc, ShiftedLeq{tp + 1, dilation, v});
+            } else if (k < 2 * n + 1) {  // B: t[:-1] - d  (may fall below 0)
                 const int i0 = k - (n + 1);
                 v = fs(tp[i0], dilation);
-                rank = i0 + partition_from(n + 1, i0 - 1, ShiftedLeq{tp, 0.f, v});         // #A <= v
-                rank += partition_from(n, i0 - 3, ShiftedLess{tp + 1, dilation, v});       // #C < v
-            } else {  // C: t[1:] + d
+                const int na = partition_from(n + 1, i0 - 1, ShiftedLeq{tp, 0.f, v});          // #A <= v
+                const int nc = partition_from(n, i0 - 3, ShiftedLess{tp + 1, dilation, v});    // #C < v
+                rank = i0 + na + nc;
+                if (v >= 0.f) {
+                    jhi = advance_while(n, i0 + 1, ShiftedLeq{tp, -dilation, v});
+                    jlo = advance_while(n, nc, ShiftedLeq{tp + 1, dilation, v});
+                } else {
+                    jhi = partition_from(n, i0 + 1, ShiftedLeq{tp, -dilation, 0.f});
+                    jlo = partition_from(n, 0, ShiftedLeq{tp + 1, dilation, 0.f});
+                }
+            } else {  // C: t[1:] + d  (may exceed 1)
                 const int i0 = k - (2 * n + 1);
                 v = fa(tp[i0 + 1], dilation);
-                rank = i0 + partition_from(n + 1, i0 + 2, ShiftedLeq{tp, 0.f, v});         // #A <= v
-                rank += partition_from(n, i0 + 3, ShiftedLeq{tp, -dilation, v});           // #B <= v
+                const int na = partition_from(n + 1, i0 + 2, ShiftedLeq{tp, 0.f, v});          // #A <= v
+                const int nb = partition_from(n, i0 + 3, ShiftedLeq{tp, -dilation, v});        // #B <= v
+                rank = i0 + na + nb;
+                if (v <= 1.f) {
+                    jhi = nb;
+                    jlo = advance_while(n, i0 + 1, ShiftedLeq{tp + 1, dilation, v});
+                } else {
+                    jhi = partition_from(n, n, ShiftedLeq{tp, -dilation, 1.f});
+                    jlo = partition_from(n, i0, ShiftedLeq{tp + 1, dilation, 1.f});
+                }
             }
             sc.T[rank] = fminf(fmaxf(v, 0.f), 1.f);
+            sc.J[rank] = bits_to_float(((uint32_t)jhi << 16) | (uint32_t)jlo);
         }
         ex.sync();
-        // stepfun.py:L81-87: w_dilate[k] = max_j { p_j : t0_j <= T_k < t1_j } (0 if none), k < m-1;
-        // the qualifying j form a contiguous range because t0 and t1 are sorted.
+        // stepfun.py:L81-87: w_dilate[k] = max_j { p_j : t0_j <= T_k < t1_j } (0 if none), k < m-1
         double part = 0.0;
         for (int k = lane; k < m - 1; k += st) {
             const float Tk = sc.T[k];
-            // merged position k holds roughly every third fencepost: k / 3 is a good first guess for both counts
-            const int jhi = partition_from(n, k / 3 + 1, ShiftedLeq{tp, -dilation, Tk});      // #{j : t0_j <= Tk}
-            const int jlo = partition_from(n, k / 3 - 1, ShiftedLeq{tp + 1, dilation, Tk});   // #{j : t1_j <= Tk}
+            const uint32_t jj = float_to_bits(sc.J[k]);
+            const int jhi = (int)(jj >> 16), jlo = (int)(jj & 0xffffu);
             float pm = 0.f;
             for (int j = jlo; j < jhi; ++j) pm = fmaxf(pm, sc.pp[j]);
             const float w = fm(pm, fs(sc.T[k + 1], Tk));  // pdf_to_weight, stepfun.py:L69-72

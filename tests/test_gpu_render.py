@@ -104,6 +104,12 @@ def test_host_entry_equals_device_entry():
     out = r.render_rays_host(hb, 1.0, want=("rgb", "depth", "acc", "packed", "weights_1"))
     for k in ("rgb", "depth", "acc", "packed", "weights_1"):
         assert np.array_equal(out[k].numpy(), dev[k]), k
+    # several chunks: the host entry pipelines the copies of neighbouring chunks under each chunk's kernels
+    r.set_option("chunk_rays", 37)
+    out = r.render_rays_host(hb, 1.0, want=("rgb", "depth", "acc", "packed", "weights_1", "sdist_0", "sdist_1"))
+    r.set_option("chunk_rays", 131072)
+    for k in ("rgb", "depth", "acc", "packed", "weights_1", "sdist_0", "sdist_1"):
+        assert np.array_equal(out[k].numpy(), dev[k]), k
 
 
 def test_chunking_and_permutation_invariance():

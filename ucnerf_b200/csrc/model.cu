@@ -76,6 +76,8 @@ struct ucnerf_model {
     DevBuf density, h1, rgb_s;
     // host-entry staging
     DevBuf stage_in, stage_out, cam_rays;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host entry: H2D / D2H overlap the render stream chunk by chunk
+    std::vector<cudaEvent_t> ev_in, ev_done;
     int64_t chunk_rays = 131072;
     int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 FP16 split (error if shapes unsupported), 2 = auto
     bool use_affine = false;
@@ -478,6 +480,10 @@ extern "C" int ucnerf_model_destroy(ucnerf_model* m) {
         b->release();
     resolve_timing(m);
     for (auto& e : m->pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto e : m->ev_in) cudaEventDestroy(e);
+    for (auto e : m->ev_done) cudaEventDestroy(e);
+    if (m->copy_in) cudaStreamDestroy(m->copy_in);
+    if (m->copy_out) cudaStreamDestroy(m->copy_out);
     delete m;
     return 0;
 }
@@ -602,6 +608,54 @@ static int camera_rays(ucnerf_model* m, const ucnerf_camera* cam, uint32_t row0,
 
 }  // namespace ucnerf
 
+// Chunk pipeline of the host entries: the H2D copies of chunk c+1 (when `srcs` is given) and the D2H copies of chunk
+// c-1 run on their own streams under chunk c's kernels.  The caller holds m->mu.
+static int render_pipelined(ucnerf_model* m, size_t N, const ucnerf_rays& rd, const float* const* srcs, float* const* dsts,
+                            const size_t* widths, double train_frac, const ucnerf_outputs& od, std::vector<OutSlot>& slots,
+                            cudaStream_t st) {
+    // ---- chunk pipeline: the copies of chunk c+1 (in) and c-1 (out) run on their own streams under chunk c's kernels ----
+    if (!m->copy_in) {
+        UC_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_in, cudaStreamNonBlocking));
+        UC_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_out, cudaStreamNonBlocking));
+    }
+    const size_t chunk = (size_t)m->chunk_rays;
+    const size_t nchunks = (N + chunk - 1) / chunk;
+    while (m->ev_in.size() < nchunks + 1) {
+        cudaEvent_t a, b;
+        UC_CUDA_OK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        UC_CUDA_OK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        m->ev_in.push_back(a);
+        m->ev_done.push_back(b);
+    }
+    // the copy streams start after whatever the caller queued on `st` before this call
+    UC_CUDA_OK(cudaEventRecord(m->ev_in[nchunks], st));
+    UC_CUDA_OK(cudaStreamWaitEvent(m->copy_in, m->ev_in[nchunks], 0));
+    UC_CUDA_OK(cudaStreamWaitEvent(m->copy_out, m->ev_in[nchunks], 0));
+    for (size_t c = 0; c < nchunks; ++c) {
+        const size_t r0 = c * chunk, n = std::min(chunk, N - r0);
+        if (srcs)
+            for (int i = 0; i < 8; ++i)
+                UC_CUDA_OK(cudaMemcpyAsync(dsts[i] + r0 * widths[i], srcs[i] + r0 * widths[i], n * widths[i] * sizeof(float),
+                                           cudaMemcpyHostToDevice, m->copy_in));
+        UC_CUDA_OK(cudaEventRecord(m->ev_in[c], m->copy_in));
+    }
+    for (size_t c = 0; c < nchunks; ++c) {
+        const size_t r0 = c * chunk, n = std::min(chunk, N - r0);
+        UC_CUDA_OK(cudaStreamWaitEvent(st, m->ev_in[c], 0));
+        if (int e = render_chunk(m, (uint32_t)n, rd, r0, train_frac, od, st)) return e;
+        UC_CUDA_OK(cudaEventRecord(m->ev_done[c], st));
+        UC_CUDA_OK(cudaStreamWaitEvent(m->copy_out, m->ev_done[c], 0));
+        for (auto& sl : slots) {
+            const size_t per = sl.floats / N;
+            UC_CUDA_OK(cudaMemcpyAsync(sl.host + r0 * per, *sl.dev_field + r0 * per, n * per * sizeof(float),
+                                       cudaMemcpyDeviceToHost, m->copy_out));
+        }
+    }
+    UC_CUDA_OK(cudaStreamSynchronize(m->copy_out));
+    UC_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" int ucnerf_generate_rays(const ucnerf_camera* cam, uint32_t row0, uint32_t n_rows, const ucnerf_ray_buffers* out,
                                     void* stream) {
     UC_REQUIRE(cam && out, "generate_rays: null argument");
@@ -636,10 +690,15 @@ extern "C" int ucnerf_render_camera_host(ucnerf_model* m, const ucnerf_camera* c
     UC_REQUIRE(m && cam && oh, "render_camera_host: null argument");
     if (n_rows == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(m->mu);
+    const size_t N = (size_t)n_rows * cam->width;
     ucnerf_outputs od{};
     std::vector<OutSlot> slots;
-    if (int e = stage_outputs(m, (size_t)n_rows * cam->width, oh, od, slots)) return e;
-    if (int e = ucnerf_render_camera(m, cam, row0, n_rows, train_frac, &od, stream)) return e;
+    if (int e = stage_outputs(m, N, oh, od, slots)) return e;
+    ucnerf_rays rd{};
+    if (int e = camera_rays(m, cam, row0, n_rows, rd, st)) return e;      // one kernel on the render stream
+    if (int e = render_pipelined(m, N, rd, nullptr, nullptr, nullptr, train_frac, od, slots, st)) return e;
+    slots.clear();
     return copy_back_and_check(m, slots, st);
 }
 
@@ -652,7 +711,8 @@ extern "C" int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const u
                "render_rays_host: every ray array (incl. rand_vec) must be provided");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t N = (size_t)n_rays;
-    // ---- stage inputs: 5 x [N,3] + 3 x [N] floats ----
+    std::lock_guard<std::mutex> lk(m->mu);
+    // ---- staging: 5 x [N,3] + 3 x [N] floats in, the requested outputs out ----
     if (int e = m->stage_in.ensure(N * 18 * sizeof(float))) return e;
     float* base = m->stage_in.as<float>();
     ucnerf_rays rd{};
@@ -660,18 +720,14 @@ extern "C" int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const u
     const size_t widths[8] = {3, 3, 3, 3, 3, 1, 1, 1};
     float* dsts[8];
     size_t off = 0;
-    for (int i = 0; i < 8; ++i) {
-        dsts[i] = base + off;
-        UC_CUDA_OK(cudaMemcpyAsync(dsts[i], srcs[i], N * widths[i] * sizeof(float), cudaMemcpyHostToDevice, st));
-        off += N * widths[i];
-    }
+    for (int i = 0; i < 8; ++i) { dsts[i] = base + off; off += N * widths[i]; }
     rd.origins = dsts[0]; rd.directions = dsts[1]; rd.viewdirs = dsts[2]; rd.cam_dirs = dsts[3]; rd.rand_vec = dsts[4];
     rd.radii = dsts[5]; rd.near = dsts[6]; rd.far = dsts[7];
-    // ---- stage outputs ----
     ucnerf_outputs od{};
     std::vector<OutSlot> slots;
     if (int e = stage_outputs(m, N, oh, od, slots)) return e;
-    if (int e = ucnerf_render_rays(m, n_rays, &rd, train_frac, &od, stream)) return e;
+    if (int e = render_pipelined(m, N, rd, srcs, dsts, widths, train_frac, od, slots, st)) return e;
+    slots.clear();
     return copy_back_and_check(m, slots, st);
 }
 

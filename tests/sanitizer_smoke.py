@@ -1,3 +1,5 @@
+"""Small end-to-end run for `compute-sanitizer --tool memcheck python tests/sanitizer_smoke.py` on the GPU box: the render
+path on two configurations, the sky head and the ray generator (profiles/r1_sanitizer_memcheck.txt: 0 errors)."""
 import sys, torch, numpy as np
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 from oracle import cases, ucnerf_oracle as O

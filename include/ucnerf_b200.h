@@ -69,6 +69,15 @@ int ucnerf_grad_total_variation(const void* inputs, const void* embeddings, void
                                 uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
                                 int dtype, void* stream);
 
+/* Fused optimiser step for one GridEncoder table: hash-decay gradient
+ * (models.py:L297-306 with train_utils.py:L301-305 `hash_decay_mults`), grad.nan_to_num_() (train_utils.py:L344-345),
+ * torch.optim.Adam as train_utils.create_optimizer builds it (L347-366: betas, eps, no weight decay, no amsgrad) and
+ * zero_grad (train.py:L164) in ONE pass over embeddings / grad / exp_avg / exp_avg_sq [sum T, C] (device, fp32, C = 4).
+ * offsets_host [L+1] as in GridEncoder.offsets; `step` counts from 1; hash_decay_mult = 0 gives plain Adam. */
+int ucnerf_grid_adam_step(float* embeddings, float* grad, float* exp_avg, float* exp_avg_sq,
+                          const int32_t* offsets_host, uint32_t L, uint32_t C, double lr, double beta1, double beta2,
+                          double eps, uint64_t step, double hash_decay_mult, int zero_grad, void* stream);
+
 /* ---- fused forward render (eval path, rand=False) ---- */
 
 /* One MLP's GridEncoder + density_layer (models.py:L425-441).  Pointers are device pointers to the

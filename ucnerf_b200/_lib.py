@@ -98,6 +98,7 @@ EXPORTS = [
     "ucnerf_render_rays", "ucnerf_render_rays_host", "ucnerf_launch_count", "ucnerf_set_option",
     "ucnerf_get_timing", "ucnerf_generate_rays", "ucnerf_render_camera", "ucnerf_render_camera_host",
     "ucnerf_set_rgb_affine", "ucnerf_sky_create", "ucnerf_sky_destroy", "ucnerf_sky_render",
+    "ucnerf_grid_adam_step",
 ]
 
 _lib = None
@@ -136,6 +137,8 @@ def load():
     lib.ucnerf_render_camera.argtypes = [vp, C.POINTER(Camera), u32, u32, C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_render_camera_host.argtypes = [vp, C.POINTER(Camera), u32, u32, C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_set_rgb_affine.argtypes = [vp, vp]
+    lib.ucnerf_grid_adam_step.argtypes = [vp, vp, vp, vp, vp, u32, u32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                          C.c_uint64, C.c_double, C.c_int, vp]
     lib.ucnerf_sky_create.argtypes = [C.POINTER(SkyDesc), C.POINTER(vp)]
     lib.ucnerf_sky_destroy.argtypes = [vp]
     lib.ucnerf_sky_render.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_double, vp, vp]

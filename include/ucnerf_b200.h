@@ -160,6 +160,8 @@ typedef struct ucnerf_outputs {
     float* packed;                /* [N,12] (rgb[3], depth, acc, distance_mean, distance_median, distance_percentile_5,
                                      distance_percentile_95, depth_raw, 0, 0): the one buffer the multi-GPU
                                      tile all-gather moves */
+    float* sample_coord;          /* [N, S_nerf, 3] `coord` of the NeRF level (models.py:L512,L677): mean of the six
+                                     contracted multisample positions / 2 */
 } ucnerf_outputs;
 
 /* Rays and outputs in device memory.  train_frac only enters through the anneal (models.py:L179-184). */

@@ -30,7 +30,7 @@ def run(name):
     for lvl in range(cfg.num_levels):
         for k in rr[lvl]:
             assert torch.equal(rr[lvl][k], orr[lvl][k]), (name, lvl, k)
-        for k in ("sdist", "weights", "density", "rgb"):
+        for k in ("sdist", "weights", "density", "rgb", "coord"):
             assert torch.equal(rh[lvl][k], oh[lvl][k]), (name, lvl, k)
         out[f"sdist_{lvl}"] = rh[lvl]["sdist"].numpy()
         out[f"weights_{lvl}"] = rh[lvl]["weights"].numpy()
@@ -42,6 +42,7 @@ def run(name):
     assert np.array_equal(out["depth_raw"][out["acc"] >= 0.6], out["depth"][out["acc"] >= 0.6])
     out["sample_rgb"] = rh[-1]["rgb"].numpy()
     out["sample_density"] = rh[-1]["density"].numpy()
+    out["sample_coord"] = rh[-1]["coord"].numpy()
     cs = cases.param_checksums(params)
     out["checksum_keys"] = np.array(sorted(cs))
     out["checksum_vals"] = np.array([cs[k] for k in sorted(cs)], dtype=np.float64)

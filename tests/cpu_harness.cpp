@@ -67,6 +67,26 @@ void h_cone_points(int n_rays, int S, const float* origins, const float* directi
     }
 }
 
+// out_c [N,S,3]: `coord` of every interval (mean of the six contracted multisample means / 2)
+void h_sample_coord(int n_rays, int S, const float* origins, const float* directions, const float* cam_dirs,
+                    const float* rand_vec, const float* radii, const float* near, const float* far, const float* sdist,
+                    float std_scale, float* out_c) {
+    ConeTable ct;
+    make_cone_table(ct);
+    for (int r = 0; r < n_rays; ++r) {
+        RayGeom rg;
+        make_ray_geom(rg, origins + 3 * r, directions + 3 * r, cam_dirs + 3 * r, rand_vec + 3 * r, radii[r], near[r], far[r]);
+        for (int s = 0; s < S; ++s) {
+            const float s0 = sdist[(size_t)r * (S + 1) + s], s1 = sdist[(size_t)r * (S + 1) + s + 1];
+            const float t0 = fa(fm(s0, rg.far), fm(fs(1.f, s0), rg.near));
+            const float t1 = fa(fm(s1, rg.far), fm(fs(1.f, s1), rg.near));
+            float c[3];
+            interval_coord(rg, t0, t1, ct, s & 1, std_scale, c);
+            for (int i = 0; i < 3; ++i) out_c[((size_t)r * S + s) * 3 + i] = c[i];
+        }
+    }
+}
+
 // camera -> rays for rows [row0, row0 + n_rows): out_dir / out_view [n,3], out_plane [n,2], out_radius [n]; normals [n,4]
 void h_pixel_rays(const double* pixtocam, const double* camtoworld, int width, int height, int row0, int n_rows,
                   uint64_t seed, float* out_dir, float* out_view, float* out_plane, float* out_radius, float* normals) {

@@ -35,6 +35,7 @@ class FakeRenderer:
             out[f"sdist_{l}"] = torch.linspace(0, 1, S + 1).expand(n, S + 1).contiguous()
             out[f"weights_{l}"] = o[:, :1].expand(n, S).contiguous()
         out["sample_rgb"] = o[:, None, :].expand(n, self.samples[-1], 3).contiguous()
+        out["sample_coord"] = (o[:, None, :] * 0.5).expand(n, self.samples[-1], 3).contiguous()
         return {k: out[k] for k in want}
 
 
@@ -95,6 +96,7 @@ def main():
         assert torch.equal(img["depth"], origins.sum(-1)) and torch.equal(img["acc"], origins[..., 0] * 2)
         assert torch.equal(img["distance_percentile_95"], origins[..., 1] + 8)
         assert img["weights"].shape == (H, W, 4) and torch.equal(img["weights"][..., 0], origins[..., 0])
+        assert img["coord"].shape == (H, W, 4, 3) and torch.equal(img["coord"][:, :, 2, :], origins * 0.5)
         assert len(img["ray_sdist"]) == 2 and img["ray_rgbs"][0].shape == (4, 8, 3)
         # heads of the shipped config on top (sky through the reference-module path, brightness affines): the sharded
         # result must equal the single-process one

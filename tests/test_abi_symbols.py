@@ -33,7 +33,7 @@ def test_struct_sizes_match_header(lib):
     assert ctypes.sizeof(_lib.MlpDesc) == 3 * 8 + 4 * 4 + 4 * 8
     assert ctypes.sizeof(_lib.ModelDesc) == 6 * 4 + 8 * 8 + 5 * ctypes.sizeof(_lib.MlpDesc) + 6 * 8
     assert ctypes.sizeof(_lib.Rays) == 8 * 8
-    assert ctypes.sizeof(_lib.Outputs) == (8 + 5 + 5 + 3) * 8
+    assert ctypes.sizeof(_lib.Outputs) == (8 + 5 + 5 + 4) * 8
     assert ctypes.sizeof(_lib.Camera) == 21 * 8 + 4 * 4 + 8
     assert ctypes.sizeof(_lib.RayBuffers) == 9 * 8
 

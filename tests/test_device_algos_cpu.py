@@ -150,3 +150,18 @@ def test_fused_path_hash_lookup_matches_kernel_restatement(harness):
     harness.h_grid_features(512, L, _fp(desc), _fp(emb), _fp(x), _fp(out))
     ref, _ = O.grid_encode_forward(x, emb, offs, 512, 3, 4, L, 1.0, 16)
     assert np.array_equal(out, ref.transpose(1, 0, 2))
+
+
+def test_sample_coord_matches_reference_golden(harness):
+    """`coord` of the NeRF level (models.py:L512,L677) from the device algorithm against the reference's own values."""
+    from conftest import load_golden
+    g = load_golden("waymo")
+    n, S = g["sample_coord"].shape[:2]
+    arr = lambda k: np.ascontiguousarray(g["batch_" + k], np.float32)
+    sd = np.ascontiguousarray(g[f"sdist_{1}"], np.float32)
+    out = np.zeros((n, S, 3), np.float32)
+    harness.h_sample_coord(n, S, _fp(arr("origins")), _fp(arr("directions")), _fp(arr("cam_dirs")), _fp(arr("rand_vec")),
+                           _fp(arr("radii").reshape(-1)), _fp(arr("near").reshape(-1)), _fp(arr("far").reshape(-1)), _fp(sd),
+                           cf(0.5), _fp(out))
+    err = np.abs(out - g["sample_coord"]).max()
+    assert err < 3e-7, err

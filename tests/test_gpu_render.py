@@ -31,7 +31,7 @@ def build_renderer(cfg, params):
 
 
 ALL = ["rgb", "depth", "depth_raw", "acc", "distance_mean", "distance_median", "distance_percentile_5",
-       "distance_percentile_95", "sample_rgb", "sample_density", "packed"]
+       "distance_percentile_95", "sample_rgb", "sample_density", "packed", "sample_coord"]
 
 
 def run(r, batch, extra=()):
@@ -79,6 +79,8 @@ def test_render_matches_reference_golden(name):
     assert np.array_equal(p[:, 0:3], out["rgb"]) and np.array_equal(p[:, 3], out["depth"])
     assert np.array_equal(p[:, 4], out["acc"]) and np.array_equal(p[:, 9], out["depth_raw"])
     np.testing.assert_allclose(out["sample_rgb"], g["sample_rgb"], atol=5e-4)
+    # `coord` of the NeRF level; positions follow the fenceposts, which carry the resampler's ~1e-6 round-off
+    assert np.abs(out["sample_coord"] - g["sample_coord"]).max() < 2e-5
 
 
 @pytest.mark.parametrize("name,n,seed", [("config1", 4096, 7), ("waymo", 1024, 8)])

@@ -72,6 +72,7 @@ class Outputs(C.Structure):
         ("sdist", C.c_void_p * (MAX_PROP_LEVELS + 1)),
         ("weights", C.c_void_p * (MAX_PROP_LEVELS + 1)),
         ("sample_rgb", C.c_void_p), ("sample_density", C.c_void_p), ("packed", C.c_void_p),
+        ("sample_coord", C.c_void_p),
     ]
 
 

@@ -389,6 +389,8 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         if (int e = time_begin(m, st)) return e;
         if (int e = launch_sample_encode(sp, nerf, st)) return e;
         if (int e = time_end(m, st, nerf ? 2 : 1)) return e;
+        if (nerf && o.sample_coord)
+            if (int e = launch_sample_coord(sp, o.sample_coord + ray0 * S * 3, st)) return e;
 
         if (nerf) {
             ColorParams cp{};
@@ -554,6 +556,7 @@ static int stage_outputs(ucnerf_model* m, size_t N, const ucnerf_outputs* oh, uc
     add(oh->sample_rgb, (size_t)m->lv[nl - 1].S * 3, &od.sample_rgb);
     add(oh->sample_density, (size_t)m->lv[nl - 1].S, &od.sample_density);
     add(oh->packed, 12, &od.packed);
+    add(oh->sample_coord, (size_t)m->lv[nl - 1].S * 3, &od.sample_coord);
     size_t tot = 0;
     for (auto& s : slots) tot += (s.floats + 3) & ~size_t(3);
     if (int e = m->stage_out.ensure(std::max<size_t>(tot, 4) * sizeof(float))) return e;

@@ -447,8 +447,9 @@ UC_HD ConeInterval make_cone_interval(float t0, float t1) {
 
 // One multisample point -> unit-cube grid coordinate g in [0,1]^3 and contracted std (already /2).
 // render.py:L116-148 (point), coord.py:L60-72 (contract), models.py:L489-493 (/2), grid.py:L162 ((x+1)/2).
+// xh (optional): the contracted mean / 2 itself (models.py:L491 `means / bound`), the `coord` the reference reports.
 UC_HD void cone_point(const RayGeom& rg, const ConeInterval& ci, const ConeTable& ct, int j, int odd, float std_scale,
-                      float (&g)[3], float& sigma) {
+                      float (&g)[3], float& sigma, float* xh = nullptr) {
     const float t = fa(ci.t0, fm(ci.tdA, fa(ci.B, fm(ct.tcoef[j], ci.Cq))));
     const float rt = fm(rg.radius, t);
     // the lateral offsets (|px|,|py| ~ 1e-4 t) and the std only need relative accuracy ~1e-7: multiply by 1/sqrt(2)
@@ -478,6 +479,23 @@ UC_HD void cone_point(const RayGeom& rg, const ConeInterval& ci, const ConeTable
     sigma = fm(sd, 0.5f);
 #pragma unroll
     for (int i = 0; i < 3; ++i) g[i] = fm(fa(fm(x[i], 0.5f), 1.f), 0.5f);
+    if (xh) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) xh[i] = fm(x[i], 0.5f);
+    }
+}
+
+// models.py:L512 `means.mean(dim=-2)` of one interval: the six contracted multisample means / 2, averaged ("coord",
+// models.py:L677, consumed by extract.py through render_image(return_weights=True))
+UC_HD void interval_coord(const RayGeom& rg, float t0, float t1, const ConeTable& ct, int odd, float std_scale, float (&c)[3]) {
+    const ConeInterval ci = make_cone_interval(t0, t1);
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int j = 0; j < 6; ++j) {
+        float g[3], sg, xh[3];
+        cone_point(rg, ci, ct, j, odd, std_scale, g, sg, xh);
+        for (int i = 0; i < 3; ++i) acc[i] = j == 0 ? xh[i] : fa(acc[i], xh[i]);
+    }
+    for (int i = 0; i < 3; ++i) c[i] = fd(acc[i], 6.f);
 }
 
 // ---- hash-grid lookup on the fused path (D=3, C=4, gridtype=hash, align_corners=False, linear) --

@@ -45,6 +45,35 @@ int launch_resample(const ResampleParams& p, cudaStream_t st) {
 }
 
 // =================================================================================================
+// 2b. sample coordinates ("coord" of ray_history, models.py:L677): only launched when the caller asks for them
+//     (render_image(return_weights=True) for extract.py); thread = (ray, sample)
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+sample_coord_kernel(const __grid_constant__ SampleParams p, float* __restrict__ out) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (size_t)p.n_rays * p.S) return;
+    const uint32_t ray = (uint32_t)(q / p.S);
+    const int s = (int)(q - (size_t)ray * p.S);
+    RayGeom rg;
+    make_ray_geom(rg, p.rays.origins + 3 * (size_t)ray, p.rays.directions + 3 * (size_t)ray, p.rays.cam_dirs + 3 * (size_t)ray,
+                  p.rays.rand_vec + 3 * (size_t)ray, p.rays.radii[ray], p.rays.near[ray], p.rays.far[ray]);
+    const float s0 = p.sdist[(size_t)ray * p.sdist_stride + s], s1 = p.sdist[(size_t)ray * p.sdist_stride + s + 1];
+    const float t0 = fa(fm(s0, rg.far), fm(fs(1.f, s0), rg.near));
+    const float t1 = fa(fm(s1, rg.far), fm(fs(1.f, s1), rg.near));
+    float c[3];
+    interval_coord(rg, t0, t1, p.cone, s & 1, p.std_scale, c);
+    out[3 * q] = c[0]; out[3 * q + 1] = c[1]; out[3 * q + 2] = c[2];
+}
+
+int launch_sample_coord(const SampleParams& p, float* out, cudaStream_t st) {
+    const size_t total = (size_t)p.n_rays * p.S;
+    if (total == 0) return 0;
+    sample_coord_kernel<<<(unsigned)div_up(total, (size_t)256), 256, 0, st>>>(p, out);
+    UC_LAUNCH_CHECK();
+    return 0;
+}
+
+// =================================================================================================
 // 3. colour MLP, fp32 SIMT path: 64-row tiles, register-tiled GEMM chain in shared memory.
 //    Reference (models.py:L587-674): x = W2 h1 + b2 ; in = [x, direnc] ; a = relu(V0 in + c0) ;
 //    a2 = relu(V1 [a, in] + c1) ; rgb = sigmoid(R a2 + r0) * (1 + 2 pad) - pad.  The bottleneck x has no

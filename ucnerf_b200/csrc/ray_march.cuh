@@ -120,6 +120,7 @@ struct CompositeParams {
 int launch_generate_rays(const CameraConst& cam, uint32_t row0, uint32_t n_rows, const RayOutPtrs& o, cudaStream_t st);
 int launch_resample(const ResampleParams& p, cudaStream_t st);
 int launch_sample_encode(const SampleParams& p, bool nerf, cudaStream_t st);
+int launch_sample_coord(const SampleParams& p, float* out, cudaStream_t st);
 int launch_color_mlp_simt(const ColorParams& p, int np, cudaStream_t st);
 int launch_composite(const CompositeParams& p, cudaStream_t st);
 int launch_color_mlp_tc(const ColorTcParams& p, cudaStream_t st);

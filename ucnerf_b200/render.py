@@ -226,7 +226,8 @@ class HotPathModel:
         S = self.samples
         spec = {"rgb": (n, 3), "depth": (n,), "depth_raw": (n,), "acc": (n,), "distance_mean": (n,),
                 "distance_median": (n,), "distance_percentile_5": (n,), "distance_percentile_95": (n,),
-                "sample_rgb": (n, S[-1], 3), "sample_density": (n, S[-1]), "packed": (n, PACKED_WIDTH)}
+                "sample_rgb": (n, S[-1], 3), "sample_density": (n, S[-1]), "packed": (n, PACKED_WIDTH),
+                "sample_coord": (n, S[-1], 3)}
         for l in range(self.num_levels):
             spec[f"sdist_{l}"] = (n, S[l] + 1)
             spec[f"weights_{l}"] = (n, S[l])
@@ -332,7 +333,7 @@ class HotPathModel:
         flat = {k: batch[k].reshape(-1, batch[k].shape[-1]) for k in _RAY_KEYS}
         if rand_vec is None and batch.get('rand_vec') is not None:
             rand_vec = batch['rand_vec'].reshape(-1, 3)
-        want = ["rgb", "depth", "acc", "sample_rgb", "sample_density"]
+        want = ["rgb", "depth", "acc", "sample_rgb", "sample_density", "sample_coord"]
         if compute_extras:
             want += ["distance_mean", "distance_median", "distance_percentile_5", "distance_percentile_95"]
         for l in range(self.num_levels):
@@ -358,6 +359,7 @@ class HotPathModel:
             if last:
                 h["rgb"] = out["sample_rgb"].reshape(lead + out["sample_rgb"].shape[1:])
                 h["density"] = out["sample_density"].reshape(lead + (-1,))
+                h["coord"] = out["sample_coord"].reshape(lead + out["sample_coord"].shape[1:])
             history.append(h)
         if compute_extras:  # models.py:L313-324: proposal levels show the final average colour
             final_rgb = torch.sum(renderings[-1]['ray_rgbs'] * renderings[-1]['ray_weights'][..., None], dim=-2)
@@ -491,6 +493,8 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
         r.set_rgb_affine(affine)    # reset below once the image is rendered
     nl = r.num_levels
     want = ["packed"] + [f"sdist_{l}" for l in range(nl)] + [f"weights_{l}" for l in range(nl)] + ["sample_rgb"]
+    if return_weights:
+        want.append("sample_coord")
     out = r.render_rays(local, train_frac, lrv, want)
     packed = out["packed"]
     sky_rgbs = None
@@ -525,6 +529,14 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
         wl = fw[:num_rays]
     if world == 1 or return_weights:
         rendering["weights"] = wl.reshape(height, width, -1)
+    if return_weights:   # models.py:L976-978: the NeRF level's sample coordinates for extract.py
+        co = out["sample_coord"].reshape(out["sample_coord"].shape[0], -1)
+        if world > 1:
+            import torch.distributed as dist
+            fc = torch.empty((world * per, co.shape[1]), device=r.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(fc, co.contiguous())
+            co = fc[:num_rays]
+        rendering["coord"] = co.reshape(height, width, -1, 3)
     # ray bundles for vis.visualize_suite: a random subset of vis_num_rays of this rank's rays per level
     nv = r.vis_num_rays
     n_local = stop - start

@@ -16,16 +16,19 @@
 // inf in the FP16 hi part and surface as NaN colours (never as silently wrong ones) - use color_mlp = 0 for such nets.
 //
 // CTA = one 128-row tile at a time (persistent over tiles), 10 warps:
-//   warps 0-7  two producer / epilogue warpgroups (thread t of a group owns row t; group g fills A slot g, i.e.
-//              the chunks with c % 2 == g).  They build the A operand chunk by chunk (64 K-elements = one 128-byte
-//              swizzle row of FP16) in shared memory in the UMMA canonical K-major SWIZZLE_128B layout (hi tile +
-//              lo tile): from global h1, or from acc3 in TMEM (tcgen05.ld -> scale + bias -> relu -> split).
-//              Finally they drain acc4, apply the rgb layer + sigmoid and write the sample colours.
+//   warps 0-7  two producer / epilogue warpgroups (thread t of a group owns row t).  They build the A operand chunk
+//              by chunk (64 K-elements = one 128-byte swizzle row of FP16) in shared memory in the UMMA canonical
+//              K-major SWIZZLE_128B layout (hi tile + lo tile): the h1 tile ONCE per tile with coalesced loads by all
+//              eight warps (it feeds steps 0 and 1), the four chunks of `a` from acc3 in TMEM (tcgen05.ld -> scale +
+//              per-ray bias -> relu -> split), group g converting columns [32 g, 32 g + 32) of every chunk.
+//              Finally they drain acc4 (group g: columns [128 g, 128 g + 128)), apply the rgb layer + sigmoid and
+//              write the sample colours.
 //   warp 8     one elected thread issues tcgen05.mma (M=128, N=256, K=16, kind::f16) and tcgen05.commit.
-//   warp 9     one elected thread streams the pre-swizzled weight chunks (hi|lo, 64 KB each) from L2 with
-//              cp.async.bulk (TMA bulk copy, completes on an mbarrier).
-// Pipelines: A ring (2 x 32 KB) and B ring (2 x 64 KB) with full/empty mbarriers; acc3/acc4 full/empty
-// mbarriers order MMA vs. TMEM drains.  TMEM: all 512 columns (acc3 = [0,256), acc4 = [256,512)).
+//   warp 9     one elected thread streams the pre-swizzled weight chunks (hi|lo, 64 KB each) and, per tile, the per-ray
+//              bias rows of the rays the tile touches from L2 with cp.async.bulk (completes on an mbarrier).
+// Pipelines: A ring (2 x 32 KB, slot = running chunk counter & 1, 5 chunks per tile) and B ring (2 x 64 KB) with
+// full/empty mbarriers; acc3/acc4 full/empty mbarriers order MMA vs. TMEM drains; a 2-stage ring for the bias rows.
+// TMEM: all 512 columns (acc3 = [0,256), acc4 = [256,512)).
 #include <cuda_fp16.h>
 
 #include <cmath>

@@ -2,16 +2,16 @@
 //   render.cast_rays -> coord.contract -> GridEncoder (6 points x L levels x 8 corners) -> erf pooling ->
 //   density_layer -> softplus          (models.py:L208-230, L485-512, L581; gridencoder.cu:L87-197)
 //
-// B200 notes (profiles/r1_*): the 128-bit gathers of one warp hit up to 32 different 128-byte lines per LDG, so
-// the kernel runs at the L1 wavefront limit (~1 line per clock per SM) with instruction issue as the second
-// limiter; DRAM traffic is far below the algorithmic gather bytes because the proposal table (101 MB) stays
-// L2-resident and the 6 multisample points / neighbouring samples share cells on the coarse levels.  Hence:
+// B200 notes (profiles/r1_summary.md): the proposal level is bound by instruction issue / the FP32 pipe (about 115
+// instructions per point-level, 8 of them loads), the NeRF level by L1 wavefronts (distinct 128-byte lines per gather
+// instruction) and L1-miss latency; DRAM traffic is far below the algorithmic gather bytes because the proposal table
+// (101 MB) stays L2-resident and neighbouring rays share cells on the coarse levels.  Hence:
 //   * per-level code is specialised at compile time (dense index without modulo vs. XOR-prime hash + mask),
 //     corner indices are built from shared partial terms, all 8 gathers of a point-level are issued before use;
 //   * per-level constants come from the constant bank (__grid_constant__ params), weights of the 24/40 -> 64
 //     layer from shared memory as broadcast LDS.128;
-//   * blocks of 128 threads = 128 consecutive samples of (at most two) rays, so lanes of a warp touch
-//     neighbouring cells.
+//   * a warp = 32 neighbouring rays at the SAME sample index (see sample_pos), so the lanes of one gather fall into
+//     a few lines on most levels.
 #include "ray_march.cuh"
 
 namespace ucnerf {

@@ -490,12 +490,16 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
         idx_t = torch.as_tensor(eval_camidx).reshape(-1)[:1].to(next(m.brightness_corr.parameters()).device)
         res = m.brightness_corr(indices=idx_t.repeat(2))          # .squeeze() in the reference needs >= 2 indices
         affine, affine_sky = (res[0][0], res[1][0]) if use_sky else (res[0], None)
-        r.set_rgb_affine(affine)    # reset below once the image is rendered
+        r.set_rgb_affine(affine)    # reset right after this image's render_rays
     nl = r.num_levels
     want = ["packed"] + [f"sdist_{l}" for l in range(nl)] + [f"weights_{l}" for l in range(nl)] + ["sample_rgb"]
     if return_weights:
         want.append("sample_coord")
-    out = r.render_rays(local, train_frac, lrv, want)
+    try:
+        out = r.render_rays(local, train_frac, lrv, want)
+    finally:
+        if affine is not None:
+            r.set_rgb_affine(None)   # the affine belongs to this image only, also when the render raises
     packed = out["packed"]
     sky_rgbs = None
     if use_sky:
@@ -552,7 +556,6 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
         rendering["affine_trans"] = affine[None].expand(num_rays, 3, 4)   # models.py:L361-363
         if affine_sky is not None:
             rendering["affine_trans_sky"] = affine_sky[None].expand(num_rays, 3, 4)
-        r.set_rgb_affine(None)
     return rendering
 
 

@@ -42,7 +42,11 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    ms = timeit(lambda: head.render(o, d, far, cam), a.reps)
+    from bench import ClockSampler            # nvidia-smi clocks / throttle reasons during the timed region
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = timeit(lambda: head.render(o, d, far, cam), max(a.reps, 8))
+    clocks = sampler.stop()
     hp = {k: v.cuda() for k, v in heads.items()}
     nt = min(a.torch_rays, n)
     lin = lambda x, name: torch.nn.functional.linear(x, hp[f"skynerf.{name}.weight"], hp[f"skynerf.{name}.bias"])
@@ -83,7 +87,7 @@ def main():
     print(json.dumps({"bench": "sky_head", "rays": n, "samples_per_ray": 120, "ms": ms, "rays_per_sec": n / ms * 1e3,
                       "algorithmic_tflops": flops / ms / 1e9, "tensor_roofline_frac": flops / ms / 1e9 / peak,
                       "tensor_peak_tflops": peak, "issued_tflops_3term_fp16_split": 3 * (2.0 * 497152 * n * 120) / ms / 1e9,
-                      "pytorch_fp32_ms": ms_t, "speedup_vs_pytorch_fp32": ms_t / ms, "max_abs_diff_vs_pytorch_fp32": agree,
+                      "pytorch_fp32_ms": ms_t, "speedup_vs_pytorch_fp32": ms_t / ms, "clocks": clocks, "max_abs_diff_vs_pytorch_fp32": agree,
                       "issued_note": "497,152 MAC per sample reach the tensor cores: the activation-free feature layer is "
                                      "folded into the view layer on the host; alpha, rgb and the xyz rows stay as counted",
                       "note": "PyTorch arm = the same MLP as fp32 nn.Linear layers (cuBLAS SGEMM, TF32 off), timed on "

@@ -98,6 +98,7 @@ struct SkyTcParams {
     float rgb_b[3];
     float* raw;               // [n_rows][4] = rgb_raw, alpha_raw
     uint32_t* dbg;
+    uint32_t debug_flags;     // bit 2: in-kernel wait profiler (env UCNERF_SKY_DEBUG, development only)
 };
 
 struct CompositeParams {

@@ -25,6 +25,7 @@
 // feeds layer l.  The per-sample outputs (rgb_raw, alpha_raw) go to HBM; sky_composite_kernel integrates them per ray
 // exactly as raw2outputs does (including the reference's decreasing sample depths, models.py:L872).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "ray_march.cuh"
@@ -112,13 +113,20 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
         const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t it = 0, prev_tile = 0;
         float alpha_part = 0.f, alpha_prev = 0.f;
+        // profiling (debug_flags bit 2): thread 0 of group 0 in CTA 0 -> dbg[16..]: total, wait ACC_FULL, wait A_EMPTY, epilogue
+        const bool prof = (p.debug_flags & 4u) != 0 && t == 0 && g == 0 && blockIdx.x == 0;
+        long long pw_acc = 0, pw_slot = 0, pw_epi = 0;
+        const long long pt_begin = clock64();
         uint32_t use[2] = {0u, 0u};          // completed fills of each accumulator this thread has consumed
         int epi_acc = 0;
         uint32_t epi_use = 0;                // accumulator / fill index of the previous tile's view layer
 
         // A chunk n of the running sequence lives in slot n & 1 and is its (n >> 1)-th use
         auto wait_slot = [&](uint32_t n, uint32_t step) -> bool {
-            return mbar_wait(BAR(A_EMPTY0 + (n & 1u)), ((n >> 1) & 1u) ^ 1u, p.dbg, 2, A_EMPTY0 + (n & 1u), it, step);
+            const long long t0 = prof ? clock64() : 0;
+            const bool ok = mbar_wait(BAR(A_EMPTY0 + (n & 1u)), ((n >> 1) & 1u) ^ 1u, p.dbg, 2, A_EMPTY0 + (n & 1u), it, step);
+            if (prof) pw_slot += clock64() - t0;
+            return ok;
         };
         auto publish = [&](uint32_t n) {
             fence_proxy_async();
@@ -157,7 +165,9 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
         // drain one accumulator into four A chunks: v = act(acc k + bias8[col]); thread = (row t, 32 columns of each chunk)
         auto convert = [&](int layer, bool with_alpha, uint32_t n_first) -> bool {
             const int acc = (layer + (int)it) & 1;
+            const long long tw0 = prof ? clock64() : 0;
             if (!mbar_wait(BAR(ACC_FULL0 + acc), use[acc] & 1u, p.dbg, 1, ACC_FULL0 + acc, it, (uint32_t)layer)) return false;
+            if (prof) pw_acc += clock64() - tw0;
             use[acc] += 1;
             tc_fence_after();
             constexpr bool relu = true;
@@ -249,7 +259,9 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
             const uint32_t n0 = (uint32_t)kStepsPerTile * it;
             if (!produce_p(tile, n0)) goto teardown;
             if (it > 0) {
+                const long long te = prof ? clock64() : 0;
                 if (!final_epilogue(prev_tile, it - 1)) goto teardown;
+                if (prof) pw_epi += clock64() - te;
             }
             if (!convert(0, false, n0 + 1)) goto teardown;    // h0 -> layer 1
             if (!convert(1, false, n0 + 5)) goto teardown;    // h1 -> layer 2
@@ -270,10 +282,18 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
         if (it > 0) {
             if (!final_epilogue(prev_tile, it - 1)) goto teardown;
         }
+        if (prof) {
+            p.dbg[16] = (uint32_t)((clock64() - pt_begin) >> 10); p.dbg[17] = (uint32_t)(pw_acc >> 10);
+            p.dbg[18] = (uint32_t)(pw_slot >> 10); p.dbg[19] = (uint32_t)(pw_epi >> 10); p.dbg[20] = it;
+        }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one thread) ==================================================
         if (lane == 0) {
             uint32_t it = 0;
+            // profiling (debug_flags bit 2): cycles this thread waited per barrier kind, CTA 0 -> dbg[8..13]
+            const bool prof = (p.debug_flags & 4u) != 0 && blockIdx.x == 0;
+            long long w_epi = 0, w_b = 0, w_a = 0;
+            const long long t_begin = clock64();
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
 #pragma unroll 1
                 for (int s = 0; s < kStepsPerTile; ++s) {
@@ -286,10 +306,14 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
                     const uint32_t acc_i = (uint32_t)((layer + (int)it) & 1);
                     const bool p_step = (s == 0 || s == 17);
                     // layer 1 writes the accumulator the previous tile's view layer is drained from
+                    long long t0 = prof ? clock64() : 0;
                     if (s == 1 && !mbar_wait(BAR(EPI_DONE), (it & 1) ^ 1, p.dbg, 5, EPI_DONE, it, s)) goto teardown;
+                    if (prof) { const long long t1 = clock64(); w_epi += t1 - t0; t0 = t1; }
                     const uint32_t m = (uint32_t)kStepsPerTile * it + (uint32_t)s, slot = m & 1u, ph = (m >> 1) & 1u;
                     if (!mbar_wait(BAR(B_FULL0 + slot), ph, p.dbg, 6, B_FULL0 + slot, it, s)) goto teardown;
+                    if (prof) { const long long t1 = clock64(); w_b += t1 - t0; t0 = t1; }
                     if (!mbar_wait(BAR(A_FULL0 + slot), ph, p.dbg, 7, A_FULL0 + slot, it, s)) goto teardown;
+                    if (prof) { const long long t1 = clock64(); w_a += t1 - t0; t0 = t1; }
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + kSmemA + slot * kASlotBytes);
                     const uint32_t a_lo = a_hi + kATileBytes;
@@ -309,6 +333,10 @@ sky_mlp_tc_kernel(const __grid_constant__ SkyTcParams p) {
                     umma_commit(BAR(B_EMPTY0 + slot));
                     if (last) umma_commit(BAR(ACC_FULL0 + acc_i));
                 }
+            }
+            if (prof) {
+                p.dbg[8] = (uint32_t)((clock64() - t_begin) >> 10); p.dbg[9] = (uint32_t)(w_epi >> 10);
+                p.dbg[10] = (uint32_t)(w_b >> 10); p.dbg[11] = (uint32_t)(w_a >> 10); p.dbg[12] = it;
             }
         }
     } else {
@@ -421,6 +449,7 @@ int launch_sky_mlp_tc(const SkyTcParams& p_in, cudaStream_t st) {
     }
     SkyTcParams p = p_in;
     p.dbg = g_sky_dbg;
+    if (const char* e = getenv("UCNERF_SKY_DEBUG")) p.debug_flags = (uint32_t)atoi(e);   // profiling experiments only
     static bool configured = false;
     if (!configured) {
         UC_CUDA_OK(cudaFuncSetAttribute(sky_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal));

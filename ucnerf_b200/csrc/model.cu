@@ -84,6 +84,7 @@ struct ucnerf_model {
     float affine[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};   // BrightnessCorrection affine of the current image (row-major 3x4)
     int encode_runs = 0;  // cell-run reuse in sample_encode_kernel (bit 0 = proposal levels, bit 1 = NeRF level): measured
                           // slower on B200 (profiles/r1_summary.md), kept as an option
+    int warp_rays_log2[2] = {5, 5};  // sample_encode_kernel warp shape {proposal levels, NeRF level}: 2^k rays x 2^(5-k) samples
     bool timing = false;
     float ms[5] = {0, 0, 0, 0, 0};
     uint32_t nlaunch[5] = {0, 0, 0, 0, 0};
@@ -376,6 +377,8 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         sp.density = (nerf && o.sample_density) ? o.sample_density + ray0 * S : m->density.as<float>();
         std::memcpy(sp.g2, ls.g2, sizeof(sp.g2));
         sp.cell_runs = (m->encode_runs >> (nerf ? 1 : 0)) & 1;
+        sp.rw_log2 = m->warp_rays_log2[nerf ? 1 : 0];
+        if (S % (32 >> sp.rw_log2) != 0) sp.rw_log2 = 5;   // sample blocks must tile S
         float* rgb_s = nullptr;
         if (nerf) {
             if (int e = m->h1.ensure((size_t)n * S * 64 * sizeof(float))) return e;
@@ -496,6 +499,10 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
     if (k == "chunk_rays") { UC_REQUIRE(value >= 1, "chunk_rays must be >= 1"); m->chunk_rays = value; }
     else if (k == "color_mlp") { UC_REQUIRE(value >= 0 && value <= 2, "color_mlp: 0 = fp32 SIMT, 1 = tensor core, 2 = auto"); m->color_mode = (int)value; }
     else if (k == "encode_runs") { UC_REQUIRE(value >= 0 && value <= 3, "encode_runs: bit 0 = proposal levels, bit 1 = NeRF level"); m->encode_runs = (int)value; }
+    else if (k == "warp_rays_prop" || k == "warp_rays_nerf") {
+        UC_REQUIRE(value == 32 || value == 16 || value == 8 || value == 4, "warp_rays_*: 32, 16, 8 or 4 rays per warp");
+        m->warp_rays_log2[k == "warp_rays_nerf" ? 1 : 0] = value == 32 ? 5 : value == 16 ? 4 : value == 8 ? 3 : 2;
+    }
     else if (k == "timing") m->timing = value != 0;
     else if (k == "tc_debug") m->tc_debug = (uint32_t)value;  // profiling experiments (results invalid when != 0)
     else { set_error("set_option: unknown key " + k); return 1; }

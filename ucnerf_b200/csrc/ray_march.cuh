@@ -45,6 +45,7 @@ struct SampleParams {
     float* density;          // [N, S]
     float* h1;               // [N*S, 64] (NeRF level only)
     float g2[16];            // float(grid_sizes[l]^2)
+    int rw_log2;             // warp shape of sample_encode_kernel: 2^rw_log2 rays x 2^(5 - rw_log2) samples (5 = 32 rays x 1)
     int cell_runs;           // 1: level-outer loop with cell-run reuse of the gathered corners (sample_encode.cu)
 };
 

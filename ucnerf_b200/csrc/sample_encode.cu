@@ -107,12 +107,16 @@ struct SamplePos {
     int s;
     bool valid;
 };
-__device__ __forceinline__ SamplePos sample_pos(size_t q, uint32_t n_rays, int S) {
+__device__ __forceinline__ SamplePos sample_pos(size_t q, uint32_t n_rays, int S, int rw_log2) {
     const size_t group = q / ((size_t)32 * S);
     const uint32_t rem = (uint32_t)(q - group * (size_t)32 * S);
+    // rw_log2 = 5: lane -> ray, warp -> sample.  rw_log2 < 5 (experiment, option "warp_rays"): a warp covers 2^rw_log2
+    // rays x 2^(5 - rw_log2) consecutive samples; the warps of a group enumerate (sample block, ray block).
+    const uint32_t lane = rem & 31u, w = rem >> 5, sw_log2 = 5u - (uint32_t)rw_log2;
+    const uint32_t ray_block = w & ((1u << sw_log2) - 1u), sample_block = w >> sw_log2;
     SamplePos sp;
-    sp.ray = (uint32_t)group * 32u + (rem & 31u);
-    sp.s = (int)(rem >> 5);
+    sp.ray = (uint32_t)group * 32u + (ray_block << rw_log2) + (lane & ((1u << rw_log2) - 1u));
+    sp.s = (int)((sample_block << sw_log2) + (lane >> rw_log2));
     sp.valid = sp.ray < n_rays;
     return sp;
 }
@@ -158,7 +162,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
     }
 
     const size_t block0 = (size_t)blockIdx.x * kSampleThreads;
-    const SamplePos me = sample_pos(block0 + threadIdx.x, p.n_rays, p.S);
+    const SamplePos me = sample_pos(block0 + threadIdx.x, p.n_rays, p.S, p.rw_log2);
     const size_t idx = (size_t)me.ray * p.S + me.s;  // row of this sample in the [N*S] buffers
     float2 F2[LMAX * 2];  // pooled features, (x,y) / (z,w) pairs per level
 #pragma unroll
@@ -366,7 +370,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
         if (NERF) {
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                const SamplePos o = sample_pos(block0 + (size_t)(sg + 32 * s), p.n_rays, p.S);
+                const SamplePos o = sample_pos(block0 + (size_t)(sg + 32 * s), p.n_rays, p.S, p.rw_log2);
                 if (o.valid) {
                     float* hrow = p.h1 + ((size_t)o.ray * p.S + o.s) * 64 + 16 * hg + 8 * half;  // permuted columns
                     *reinterpret_cast<float4*>(hrow) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
@@ -382,7 +386,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
     }
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const SamplePos o = sample_pos(block0 + (size_t)(sg + 32 * s), p.n_rays, p.S);
+        const SamplePos o = sample_pos(block0 + (size_t)(sg + 32 * s), p.n_rays, p.S, p.rw_log2);
         if (o.valid && hg == s) p.density[(size_t)o.ray * p.S + o.s] = softplus_f(raw[s] + p.b2 + p.density_bias);  // models.py:L581
     }
 }

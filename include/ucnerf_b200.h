@@ -78,6 +78,27 @@ int ucnerf_grid_adam_step(float* embeddings, float* grad, float* exp_avg, float*
                           const int32_t* offsets_host, uint32_t L, uint32_t C, double lr, double beta1, double beta2,
                           double eps, uint64_t step, double hash_decay_mult, int zero_grad, void* stream);
 
+/* Pooled hash-grid encode for training (SURVEY.md section 8a rows R4 + R10): the front end of MLP.predict_density
+ * (internal/models.py:L485-496) in one kernel each way.  means [B,M,3] / stds [B,M] are the multisample Gaussians
+ * render.cast_rays returns (M = 6), device fp32; contract != 0 applies coord.contract_mean_std (coord.py:L60-72) and the
+ * division by bound = 2 (models.py:L489-493), then GridEncoder.forward's (x + 1) / 2 (grid.py:L162), kernel_grid
+ * (gridencoder.cu:L87-197; D = 3, hash grid, align_corners = False, linear), the erf down-weighting with
+ * grid_sizes (models.py:L495) and the mean over the M points (L496):
+ *   features [B, L*C] fp32, coord [B,3] or NULL = means.mean(dim=-2) after contraction (models.py:L512).
+ * offsets_host [L+1] / grid_sizes_host [L] are HOST copies of GridEncoder.offsets / .grid_sizes; S = log2(per_level_scale),
+ * H = base_resolution as in ucnerf_grid_encode_forward.  C must be 4. */
+int ucnerf_pooled_encode_forward(const float* means, const float* stds, uint32_t B, uint32_t M, int contract,
+                                 const float* embeddings, const int32_t* offsets_host, const int32_t* grid_sizes_host,
+                                 uint32_t L, uint32_t C, float S, uint32_t H, float* features, float* coord, void* stream);
+
+/* Backward of the above with respect to the embeddings (means / stds carry no gradient: coord.track_linearize is
+ * @torch.no_grad, coord.py:L75): replaces the autograd chain mean -> mul -> permute -> kernel_grid_backward
+ * (gridencoder.cu:L248-340, grid.py:L65-89).  grad_features [B, L*C]; grad_embeddings [sum T, C] is ACCUMULATED into
+ * (caller-zeroed, like grid.py:L76). */
+int ucnerf_pooled_encode_backward(const float* grad_features, const float* means, const float* stds, uint32_t B, uint32_t M,
+                                  int contract, const int32_t* offsets_host, const int32_t* grid_sizes_host, uint32_t L,
+                                  uint32_t C, float S, uint32_t H, float* grad_embeddings, void* stream);
+
 /* ---- fused forward render (eval path, rand=False) ---- */
 
 /* One MLP's GridEncoder + density_layer (models.py:L425-441).  Pointers are device pointers to the

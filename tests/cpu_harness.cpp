@@ -6,6 +6,7 @@
 #include <cstring>
 #include <vector>
 #include "../ucnerf_b200/csrc/ray_algos.cuh"
+#include "../ucnerf_b200/csrc/pooled_algos.cuh"
 
 using namespace ucnerf;
 
@@ -134,6 +135,55 @@ void h_grid_features(int B, int L, const uint32_t* lvdesc, const float* table, c
         }
     }
 }
+}
+
+// pooled hash-grid encode (pooled_algos.cuh) for B intervals of M points, levels built by the product's own
+// make_grid_level from offsets / grid_sizes: features [B, L*4], coord [B,3] (optional)
+extern "C" void h_pooled_forward(int B, int M, int contract, int L, const int32_t* offsets, const int32_t* grid_sizes, float S,
+                                 uint32_t H, const float* table, const float* means, const float* stds, float* features,
+                                 float* coord) {
+    struct HostLoad {
+        const float* t;
+        float4 operator()(size_t e) const { return make_float4(t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]); }
+    };
+    for (int l = 0; l < L; ++l) {
+        GridLevel lv;
+        make_grid_level(lv, l, offsets[l], offsets[l + 1], S, H, grid_sizes[l]);
+        const float g2 = (float)(int32_t)((int64_t)grid_sizes[l] * grid_sizes[l]);
+        for (int b = 0; b < B; ++b) {
+            float F[4];
+            pooled_level_forward(lv, g2, means + (size_t)b * M * 3, stds + (size_t)b * M, M, contract != 0, HostLoad{table}, F);
+            std::memcpy(features + ((size_t)b * L + l) * 4, F, 16);
+        }
+    }
+    if (coord)
+        for (int b = 0; b < B; ++b) {
+            float c[3];
+            pooled_coord(means + (size_t)b * M * 3, stds + (size_t)b * M, M, contract != 0, c);
+            std::memcpy(coord + 3 * (size_t)b, c, 12);
+        }
+}
+
+// grad_table [sum T, 4] accumulated in fp64 (the CUDA instantiation uses fp32 red.add in nondeterministic order)
+extern "C" void h_pooled_backward(int B, int M, int contract, int L, const int32_t* offsets, const int32_t* grid_sizes, float S,
+                                  uint32_t H, const float* grad_features, const float* means, const float* stds,
+                                  double* grad_table) {
+    struct HostAdd {
+        double* t;
+        void operator()(size_t e, float a, float b, float c, float d) const {
+            t[4 * e] += a; t[4 * e + 1] += b; t[4 * e + 2] += c; t[4 * e + 3] += d;
+        }
+    };
+    for (int l = 0; l < L; ++l) {
+        GridLevel lv;
+        make_grid_level(lv, l, offsets[l], offsets[l + 1], S, H, grid_sizes[l]);
+        const float g2 = (float)(int32_t)((int64_t)grid_sizes[l] * grid_sizes[l]);
+        for (int b = 0; b < B; ++b) {
+            float dF[4];
+            std::memcpy(dF, grad_features + ((size_t)b * L + l) * 4, 16);
+            pooled_level_backward(lv, g2, means + (size_t)b * M * 3, stds + (size_t)b * M, M, contract != 0, dF, HostAdd{grad_table});
+        }
+    }
 }
 
 // debug variant: also returns the scratch arrays of the last ray processed (T, W(=probabilities), CW, C)

@@ -100,6 +100,8 @@ EXPORTS = [
     "ucnerf_get_timing", "ucnerf_generate_rays", "ucnerf_render_camera", "ucnerf_render_camera_host",
     "ucnerf_set_rgb_affine", "ucnerf_sky_create", "ucnerf_sky_destroy", "ucnerf_sky_render",
     "ucnerf_grid_adam_step",
+    "ucnerf_pooled_encode_forward",
+    "ucnerf_pooled_encode_backward",
 ]
 
 _lib = None
@@ -140,6 +142,8 @@ def load():
     lib.ucnerf_set_rgb_affine.argtypes = [vp, vp]
     lib.ucnerf_grid_adam_step.argtypes = [vp, vp, vp, vp, vp, u32, u32, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_uint64, C.c_double, C.c_int, vp]
+    lib.ucnerf_pooled_encode_forward.argtypes = [vp, vp, u32, u32, C.c_int, vp, vp, vp, u32, u32, C.c_float, u32, vp, vp, vp]
+    lib.ucnerf_pooled_encode_backward.argtypes = [vp, vp, vp, u32, u32, C.c_int, vp, vp, u32, u32, C.c_float, u32, vp, vp]
     lib.ucnerf_sky_create.argtypes = [C.POINTER(SkyDesc), C.POINTER(vp)]
     lib.ucnerf_sky_destroy.argtypes = [vp]
     lib.ucnerf_sky_render.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_double, vp, vp]

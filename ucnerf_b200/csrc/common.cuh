@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <math.h>
 #include <atomic>
 #include <string>
 
@@ -91,5 +92,27 @@ struct GridDesc {
     int num_levels;
     GridLevel lv[16];
 };
+
+// Level l of a GridEncoder with offsets[l..l+1], log2(per_level_scale) and base resolution (D = 3, gridtype hash,
+// align_corners = False): the per-level constants of kernel_grid (gridencoder.cu:L137-143, L50-84) precomputed on the host.
+inline void make_grid_level(GridLevel& g, int l, int32_t off0, int32_t off1, float log2_per_level_scale,
+                            uint32_t base_resolution, int64_t grid_size) {
+    g.offset = (uint32_t)off0;
+    g.hashmap_size = (uint32_t)(off1 - off0);
+    const float scale = exp2f((float)l * log2_per_level_scale) * (float)base_resolution - 1.0f;
+    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+    g.scale = scale;
+    g.stride1 = resolution + 1;
+    g.stride2 = g.stride1 * g.stride1;
+    uint32_t stride = 1;
+    for (int d = 0; d < 3 && stride <= g.hashmap_size; ++d) stride *= (resolution + 1);
+    g.hashed = stride > g.hashmap_size ? 1u : 0u;
+    g.pow2_mask = (g.hashmap_size & (g.hashmap_size - 1)) == 0 ? g.hashmap_size - 1 : 0u;
+    if (g.hashmap_size == 1) g.pow2_mask = 0;
+    g.grid_size = (float)grid_size;
+    // dense index of an in-range point: max = (res+1)^3 - 1 < hashmap_size  => no modulo needed
+    if (!g.hashed) g.mod_mode = 0;
+    else g.mod_mode = g.pow2_mask ? 1u : 2u;
+}
 
 }  // namespace ucnerf

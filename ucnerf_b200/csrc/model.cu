@@ -127,25 +127,10 @@ static int build_grid(ucnerf_model* m, int li, const ucnerf_mlp_desc& md) {
     ls.grid.table = reinterpret_cast<const float4*>(md.embeddings);
     ls.grid.num_levels = L;
     for (int l = 0; l < L; ++l) {
-        GridLevel& g = ls.grid.lv[l];
-        g.offset = (uint32_t)m->offsets[li][l];
-        g.hashmap_size = (uint32_t)(m->offsets[li][l + 1] - m->offsets[li][l]);
-        const float scale = exp2f((float)l * md.log2_per_level_scale) * (float)md.base_resolution - 1.0f;
-        const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
-        g.scale = scale;
-        g.stride1 = resolution + 1;
-        g.stride2 = g.stride1 * g.stride1;
-        uint32_t stride = 1;
-        for (int d = 0; d < 3 && stride <= g.hashmap_size; ++d) stride *= (resolution + 1);
-        g.hashed = stride > g.hashmap_size ? 1u : 0u;
-        g.pow2_mask = (g.hashmap_size & (g.hashmap_size - 1)) == 0 ? g.hashmap_size - 1 : 0u;
-        if (g.hashmap_size == 1) g.pow2_mask = 0;
         const int64_t gs = m->grid_sizes[li][l];
-        g.grid_size = (float)gs;
+        make_grid_level(ls.grid.lv[l], l, m->offsets[li][l], m->offsets[li][l + 1], md.log2_per_level_scale,
+                        (uint32_t)md.base_resolution, gs);
         ls.g2[l] = (float)(int32_t)(gs * gs);  // torch: int32 grid_sizes ** 2, promoted to fp32 in the product
-        // dense index of an in-range point: max = (res+1)^3 - 1 < hashmap_size  => no modulo needed
-        if (!g.hashed) g.mod_mode = 0;
-        else g.mod_mode = g.pow2_mask ? 1u : 2u;
     }
     ls.lmax = sample_encode_lmax(L);
     UC_REQUIRE(ls.lmax > 0, "model: unsupported number of grid levels");

@@ -99,6 +99,18 @@ int ucnerf_pooled_encode_backward(const float* grad_features, const float* means
                                   int contract, const int32_t* offsets_host, const int32_t* grid_sizes_host, uint32_t L,
                                   uint32_t C, float S, uint32_t H, float* grad_embeddings, void* stream);
 
+/* Stand-alone resampling pass of Model.forward's level loop (internal/models.py:L156-205: stepfun.max_dilate_weights
+ * L75-105 when dilate != 0, slice of the first/last bin, logits = where(dt > 0, anneal * log(w + padding), -inf),
+ * stepfun.sample_intervals L251-294 on the domain [0, 1]) for callers that keep the rest of the level in PyTorch
+ * (the training step; the result carries no gradient, models.py:L203-204).  Device fp32 pointers:
+ *   t_prev [N, n_prev+1], w_prev [N, n_prev] - the previous level's sdist / weights (both NULL with n_prev = 1 for the
+ *   first level, models.py:L143-147); u [S] - the base grid of stepfun.sample (L198-211: linspace(1/2S, 1-1/2S-eps, S) for
+ *   rand=False, linspace(0, 1-u_max, S) for rand=True); jitter [N, jitter_cols] or NULL - torch.rand(...) * max_jitter
+ *   (L212), jitter_cols = 1 (single_jitter) or S; out_sdist [N, S+1]. */
+int ucnerf_resample_intervals(const float* t_prev, const float* w_prev, uint32_t n_rays, int32_t n_prev, int dilate,
+                              float dilation, float anneal, float padding, int32_t S, const float* u, const float* jitter,
+                              int32_t jitter_cols, float* out_sdist, void* stream);
+
 /* ---- fused forward render (eval path, rand=False) ---- */
 
 /* One MLP's GridEncoder + density_layer (models.py:L425-441).  Pointers are device pointers to the

@@ -25,6 +25,20 @@ void h_resample(int n_rays, int n_prev, const float* t_prev, const float* w_prev
     }
 }
 
+// training variant: jitter [N, jitter_cols] (already scaled by max_jitter) added to the base u grid, stepfun.py:L206-212
+void h_resample_jitter(int n_rays, int n_prev, const float* t_prev, const float* w_prev, int dilate, float dilation,
+                       float anneal, float padding, int S, const float* u, const float* jitter, int jitter_cols, float* out) {
+    std::vector<float> scratch(ResampleScratch::floats(n_prev, S));
+    SerialExec ex;
+    for (int r = 0; r < n_rays; ++r) {
+        ResampleScratch sc;
+        sc.carve(scratch.data(), n_prev, S);
+        resample_ray(ex, n_prev, t_prev ? t_prev + (size_t)r * (n_prev + 1) : nullptr,
+                     w_prev ? w_prev + (size_t)r * n_prev : nullptr, dilate != 0, dilation, anneal, padding, S, u, sc,
+                     out + (size_t)r * (S + 1), jitter ? jitter + (size_t)r * jitter_cols : nullptr, jitter_cols > 1 ? 1 : 0);
+    }
+}
+
 // out_ray: [N, 10] = rgb[3], depth, depth_raw, acc, mean, median, p5, p95
 void h_composite(int n_rays, int S, const float* sdist, const float* density, const float* rgb, const float* dirs,
                  const float* near, const float* far, float bg, int extras, float* out_w, float* out_ray) {

@@ -102,6 +102,7 @@ EXPORTS = [
     "ucnerf_grid_adam_step",
     "ucnerf_pooled_encode_forward",
     "ucnerf_pooled_encode_backward",
+    "ucnerf_resample_intervals",
 ]
 
 _lib = None
@@ -144,6 +145,7 @@ def load():
                                           C.c_uint64, C.c_double, C.c_int, vp]
     lib.ucnerf_pooled_encode_forward.argtypes = [vp, vp, u32, u32, C.c_int, vp, vp, vp, u32, u32, C.c_float, u32, vp, vp, vp]
     lib.ucnerf_pooled_encode_backward.argtypes = [vp, vp, vp, u32, u32, C.c_int, vp, vp, u32, u32, C.c_float, u32, vp, vp]
+    lib.ucnerf_resample_intervals.argtypes = [vp, vp, u32, i32, C.c_int, f32, f32, f32, i32, vp, vp, i32, vp, vp]
     lib.ucnerf_sky_create.argtypes = [C.POINTER(SkyDesc), C.POINTER(vp)]
     lib.ucnerf_sky_destroy.argtypes = [vp]
     lib.ucnerf_sky_render.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_double, vp, vp]

@@ -237,9 +237,12 @@ struct ResampleScratch {
 //   t_prev [n+1], w_prev [n]: previous level's sdist / weights (NULL,NULL,n=1 for the first level:
 //   sdist=[0,1], weights=[1], models.py:L143-147).  u [S]: linspace(1/2S, 1-1/2S-eps, S).
 //   out_sdist [S+1].
+//   jit (optional, training: stepfun.py:L206-212 rand=True): jitter added to the u grid, already scaled by max_jitter;
+//   jit_stride 0 = one value for the whole ray (single_jitter), 1 = one per sample.
 template <class X>
 UC_HD void resample_ray(const X& ex, int n, const float* t_prev, const float* w_prev, bool dilate, float dilation,
-                        float anneal, float padding, int S, const float* u, ResampleScratch sc, float* out_sdist) {
+                        float anneal, float padding, int S, const float* u, ResampleScratch sc, float* out_sdist,
+                        const float* jit = nullptr, int jit_stride = 0) {
     const int lane = ex.lane;
     constexpr int st = X::kStride;
     for (int k = lane; k <= n; k += st) sc.tp[k] = t_prev ? t_prev[k] : (k == 0 ? 0.f : 1.f);
@@ -348,7 +351,8 @@ UC_HD void resample_ray(const X& ex, int n, const float* t_prev, const float* w_
     cdf_scan(ex, wq, nb, sc.CW);
     ex.sync();
     // stepfun.py:L158-160 + math.py sorted_interp: centers
-    for (int i = lane; i < S; i += st) sc.C[i] = sorted_interp_one(u[i], sc.CW, tq, nb + 1);
+    for (int i = lane; i < S; i += st)
+        sc.C[i] = sorted_interp_one(jit ? fa(u[i], jit[i * jit_stride]) : u[i], sc.CW, tq, nb + 1);
     ex.sync();
     // stepfun.py:L281-293: midpoints, reflected + clamped end fenceposts (domain [0,1])
     for (int k = lane; k <= S; k += st) {

@@ -80,14 +80,16 @@ int ucnerf_grid_adam_step(float* embeddings, float* grad, float* exp_avg, float*
 
 /* Pooled hash-grid encode for training (SURVEY.md section 8a rows R4 + R10): the front end of MLP.predict_density
  * (internal/models.py:L485-496) in one kernel each way.  means [B,M,3] / stds [B,M] are the multisample Gaussians
- * render.cast_rays returns (M = 6), device fp32; contract != 0 applies coord.contract_mean_std (coord.py:L60-72) and the
+ * render.cast_rays returns (M = 6), device fp32; flags & UCNERF_POOLED_CONTRACT applies coord.contract_mean_std (coord.py:L60-72) and the
  * division by bound = 2 (models.py:L489-493), then GridEncoder.forward's (x + 1) / 2 (grid.py:L162), kernel_grid
  * (gridencoder.cu:L87-197; D = 3, hash grid, align_corners = False, linear), the erf down-weighting with
  * grid_sizes (models.py:L495) and the mean over the M points (L496):
  *   features [B, L*C] fp32, coord [B,3] or NULL = means.mean(dim=-2) after contraction (models.py:L512).
  * offsets_host [L+1] / grid_sizes_host [L] are HOST copies of GridEncoder.offsets / .grid_sizes; S = log2(per_level_scale),
  * H = base_resolution as in ucnerf_grid_encode_forward.  C must be 4. */
-int ucnerf_pooled_encode_forward(const float* means, const float* stds, uint32_t B, uint32_t M, int contract,
+#define UCNERF_POOLED_CONTRACT 1     /* warp_fn = 'contract' and bound = 2 (models.py:L487-493) */
+#define UCNERF_POOLED_MERGE_RUNS 2   /* backward only: sum the corner weights of consecutive points that share a cell before reducing */
+int ucnerf_pooled_encode_forward(const float* means, const float* stds, uint32_t B, uint32_t M, int flags,
                                  const float* embeddings, const int32_t* offsets_host, const int32_t* grid_sizes_host,
                                  uint32_t L, uint32_t C, float S, uint32_t H, float* features, float* coord, void* stream);
 
@@ -96,7 +98,7 @@ int ucnerf_pooled_encode_forward(const float* means, const float* stds, uint32_t
  * (gridencoder.cu:L248-340, grid.py:L65-89).  grad_features [B, L*C]; grad_embeddings [sum T, C] is ACCUMULATED into
  * (caller-zeroed, like grid.py:L76). */
 int ucnerf_pooled_encode_backward(const float* grad_features, const float* means, const float* stds, uint32_t B, uint32_t M,
-                                  int contract, const int32_t* offsets_host, const int32_t* grid_sizes_host, uint32_t L,
+                                  int flags, const int32_t* offsets_host, const int32_t* grid_sizes_host, uint32_t L,
                                   uint32_t C, float S, uint32_t H, float* grad_embeddings, void* stream);
 
 /* Stand-alone resampling pass of Model.forward's level loop (internal/models.py:L156-205: stepfun.max_dilate_weights

@@ -179,7 +179,7 @@ extern "C" void h_pooled_forward(int B, int M, int contract, int L, const int32_
 }
 
 // grad_table [sum T, 4] accumulated in fp64 (the CUDA instantiation uses fp32 red.add in nondeterministic order)
-extern "C" void h_pooled_backward(int B, int M, int contract, int L, const int32_t* offsets, const int32_t* grid_sizes, float S,
+extern "C" void h_pooled_backward(int B, int M, int flags, int L, const int32_t* offsets, const int32_t* grid_sizes, float S,
                                   uint32_t H, const float* grad_features, const float* means, const float* stds,
                                   double* grad_table) {
     struct HostAdd {
@@ -195,7 +195,9 @@ extern "C" void h_pooled_backward(int B, int M, int contract, int L, const int32
         for (int b = 0; b < B; ++b) {
             float dF[4];
             std::memcpy(dF, grad_features + ((size_t)b * L + l) * 4, 16);
-            pooled_level_backward(lv, g2, means + (size_t)b * M * 3, stds + (size_t)b * M, M, contract != 0, dF, HostAdd{grad_table});
+            const bool contract = (flags & 1) != 0;
+            if (flags & 2) pooled_level_backward_runs(lv, g2, means + (size_t)b * M * 3, stds + (size_t)b * M, M, contract, dF, HostAdd{grad_table});
+            else pooled_level_backward(lv, g2, means + (size_t)b * M * 3, stds + (size_t)b * M, M, contract, dF, HostAdd{grad_table});
         }
     }
 }

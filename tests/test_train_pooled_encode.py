@@ -57,7 +57,7 @@ def test_oracle_matches_reference_autograd_vectors(case, tag):
     assert np.array_equal(np.nonzero(np.abs(ge).sum(-1))[0], g[f"{tag}_grad_rows"])
 
 
-def _harness_run(harness, params, prefix, gs, means, stds, grad_feats, contract=1):
+def _harness_run(harness, params, prefix, gs, means, stds, grad_feats, contract=1, merge_runs=False):
     emb = params[prefix + ".encoder.embeddings"].numpy()
     offs = np.ascontiguousarray(params[prefix + ".encoder.offsets"].numpy(), np.int32)
     gsz = np.ascontiguousarray(params[prefix + ".encoder.grid_sizes"].numpy(), np.int32)
@@ -73,7 +73,7 @@ def _harness_run(harness, params, prefix, gs, means, stds, grad_feats, contract=
                              _fp(m), _fp(s), _fp(feats), _fp(coord))
     ge = np.zeros((emb.shape[0], 4), np.float64)
     gf = np.ascontiguousarray(grad_feats.reshape(B, L * 4), np.float32)
-    harness.h_pooled_backward(B, M, contract, L, _fp(offs), _fp(gsz), ctypes.c_float(S), gs.base_resolution, _fp(gf),
+    harness.h_pooled_backward(B, M, contract | (2 if merge_runs else 0), L, _fp(offs), _fp(gsz), ctypes.c_float(S), gs.base_resolution, _fp(gf),
                               _fp(m), _fp(s), _fp(ge))
     return feats, coord, ge
 
@@ -90,6 +90,30 @@ def test_device_algorithm_matches_reference_vectors_on_cpu(harness, case, tag):
     ref = _dense_grad(g, tag, ge.shape[0])
     assert np.abs(ge - ref).max() <= 3e-6 * np.abs(ref).max()
     assert np.array_equal(np.nonzero(np.abs(ge).sum(-1))[0], g[f"{tag}_grad_rows"])
+
+
+@pytest.mark.parametrize("tag", ["prop", "nerf"])
+def test_run_merging_backward_gives_the_same_gradient_on_cpu(harness, case, tag):
+    """pooled_level_backward_runs: consecutive points of one cell reduced once; same rows, same values up to fp32 order -
+    and fewer reductions (counted through the number of distinct (row, value) adds is not observable here, so the
+    gradient itself and the reference vectors are the check)."""
+    g, cfg, params = case
+    prefix, gsf = TAGS[tag]
+    gs = gsf(cfg)
+    _, _, ge0 = _harness_run(harness, params, prefix, gs, g["means"], g["stds"], g[f"{tag}_grad_features"])
+    _, _, ge1 = _harness_run(harness, params, prefix, gs, g["means"], g["stds"], g[f"{tag}_grad_features"], merge_runs=True)
+    ref = _dense_grad(g, tag, ge1.shape[0])
+    assert np.abs(ge1 - ge0).max() <= 2e-6 * np.abs(ref).max()
+    assert np.abs(ge1 - ref).max() <= 3e-6 * np.abs(ref).max()
+    assert np.array_equal(np.nonzero(np.abs(ge1).sum(-1))[0], g[f"{tag}_grad_rows"])
+    # out-of-range points between in-range ones, no contraction, M = 3
+    rng = np.random.default_rng(8)
+    means = rng.uniform(-1.2, 1.2, (64, 3, 3)).astype(np.float32)
+    stds = rng.uniform(1e-4, 5e-2, (64, 3)).astype(np.float32)
+    gf = rng.standard_normal((64, gs.num_levels * 4)).astype(np.float32)
+    _, _, a = _harness_run(harness, params, prefix, gs, means, stds, gf, contract=0)
+    _, _, b = _harness_run(harness, params, prefix, gs, means, stds, gf, contract=0, merge_runs=True)
+    assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max()
 
 
 def test_device_algorithm_edge_cases_on_cpu(harness, case):
@@ -216,6 +240,30 @@ def test_cuda_equals_the_unfused_gridencoder_chain_and_errors(case):
         pooled_encode(enc, means.cpu(), stds.cpu())
     with pytest.raises(RuntimeError):
         pooled_encode(enc, means[..., :2], stds)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [6, 4])
+def test_cuda_run_merging_backward_equals_the_plain_backward(case, M):
+    from ucnerf_b200.gridencoder.pooled import pooled_encode
+    _, cfg, params = case
+    gs = cfg.prop_grids[0]
+    enc = _gpu_encoder(params, "prop_mlp_0", gs)
+    g = torch.Generator().manual_seed(40 + M)
+    B = 3000
+    t = torch.rand((B, 1, 1), generator=g) ** 2 * 7.5 + 0.02               # points of one interval close together
+    d = torch.nn.functional.normalize(torch.randn((B, 1, 3), generator=g), dim=-1)
+    means = (d * t + 2e-2 * t * torch.randn((B, M, 3), generator=g)).cuda()
+    stds = (5e-4 * t.expand(-1, M, 1)).reshape(B, M).contiguous().cuda()
+    gf = torch.randn((B, gs.num_levels * 4), generator=g).cuda()
+    grads = []
+    for merge in (False, True):
+        enc.embeddings.grad = None
+        feats, _ = pooled_encode(enc, means, stds, merge_runs=merge)
+        feats.backward(gf)
+        grads.append(enc.embeddings.grad.clone())
+    assert float((grads[0] - grads[1]).abs().max()) <= 1e-5 * float(grads[0].abs().max())
+    assert torch.equal(grads[0].abs().sum(-1) > 0, grads[1].abs().sum(-1) > 0)
 
 
 @pytest.mark.gpu

@@ -110,6 +110,51 @@ UC_HD void pooled_level_backward(const GridLevel& lv, float g2, const float* mea
     }
 }
 
+// Same scatter with the corner coefficients of CONSECUTIVE points that share a grid cell summed before they are
+// reduced: the M points of an interval are ordered along the ray and mostly stay in one cell on the coarse levels
+// (93 / 86 / 75 / 63 / 48 / 30 % of the proposal intervals on levels 0..5), so a run costs 8 reductions instead of
+// 8 per point.  dE[corner k of the run's cell] += (sum_j w_k(g_j) om_jl / M) * dF: the same value up to the order of
+// the fp32 sums.  The atomics are the limiter of the backward, not the arithmetic.
+template <class Add>
+UC_HD void pooled_level_backward_runs(const GridLevel& lv, float g2, const float* means, const float* stds, int M,
+                                      bool contract, const float (&dF)[4], const Add& add) {
+    const float inv = 1.f / (float)M;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t cx = 0, cy = 0, cz = 0;
+    bool open = false;
+#pragma unroll
+    for (int j = 0; j <= M; ++j) {
+        bool inside = false;
+        CellCoords c{};
+        float coef = 0.f;
+        if (j < M) {
+            float g[3], sigma, xh[3];
+            pooled_point(means + 3 * j, stds[j], contract, g, sigma, xh);
+            inside = in_unit_cube(g);          // gridencoder.cu:L276-281
+            if (inside) {
+                c = cell_of(lv, g);
+                coef = pooled_erf_weight(sigma, g2) * inv;
+            }
+        }
+        // close the current run when the cell changes or after the last point
+        if (open && (j == M || (inside && (c.ix != cx || c.iy != cy || c.iz != cz)))) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t idx = level_index(lv, cx + (k & 1), cy + ((k >> 1) & 1), cz + ((k >> 2) & 1));
+                add((size_t)lv.offset + idx, a[k] * dF[0], a[k] * dF[1], a[k] * dF[2], a[k] * dF[3]);
+                a[k] = 0.f;
+            }
+            open = false;
+        }
+        if (inside) {
+            cx = c.ix; cy = c.iy; cz = c.iz;
+            open = true;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fmaf(corner_weight(c, k), coef, a[k]);
+        }
+    }
+}
+
 // models.py:L512 means.mean(dim=-2) of the contracted means / 2
 UC_HD void pooled_coord(const float* means, const float* stds, int M, bool contract, float (&out)[3]) {
     float acc[3] = {0.f, 0.f, 0.f};

@@ -73,7 +73,8 @@ pooled_forward_kernel(const float* __restrict__ means, const float* __restrict__
     }
 }
 
-template <int MT>
+// RUNS: sum the corner coefficients of consecutive points in one cell before reducing (pooled_level_backward_runs)
+template <int MT, bool RUNS>
 __global__ void __launch_bounds__(kPooledThreads)
 pooled_backward_kernel(const float* __restrict__ grad_features, const float* __restrict__ means,
                        const float* __restrict__ stds, uint32_t B, int M, int contract,
@@ -87,7 +88,8 @@ pooled_backward_kernel(const float* __restrict__ grad_features, const float* __r
     float mj[3 * kPooledMaxM], sj[kPooledMaxM];
     load_interval(means, stds, b, M, mj, sj);
     const float dF[4] = {d.x, d.y, d.z, d.w};
-    pooled_level_backward(pl.lv[l], pl.g2[l], mj, sj, M, contract != 0, dF, TableRedAdd{grad_table});
+    if constexpr (RUNS) pooled_level_backward_runs(pl.lv[l], pl.g2[l], mj, sj, M, contract != 0, dF, TableRedAdd{grad_table});
+    else pooled_level_backward(pl.lv[l], pl.g2[l], mj, sj, M, contract != 0, dF, TableRedAdd{grad_table});
 }
 
 static int make_levels(PooledLevels& pl, const int32_t* offsets_host, const int32_t* grid_sizes_host, uint32_t L,
@@ -108,7 +110,7 @@ static int make_levels(PooledLevels& pl, const int32_t* offsets_host, const int3
 
 using namespace ucnerf;
 
-extern "C" int ucnerf_pooled_encode_forward(const float* means, const float* stds, uint32_t B, uint32_t M, int contract,
+extern "C" int ucnerf_pooled_encode_forward(const float* means, const float* stds, uint32_t B, uint32_t M, int flags,
                                             const float* embeddings, const int32_t* offsets_host,
                                             const int32_t* grid_sizes_host, uint32_t L, uint32_t C, float S, uint32_t H,
                                             float* features, float* coord, void* stream) {
@@ -119,6 +121,7 @@ extern "C" int ucnerf_pooled_encode_forward(const float* means, const float* std
     PooledLevels pl;
     if (int e = make_levels(pl, offsets_host, grid_sizes_host, L, S, H)) return e;
     const dim3 grid(div_up(B, (uint32_t)kPooledThreads), L, 1);
+    const int contract = flags & UCNERF_POOLED_CONTRACT;
     if (M == 6)
         pooled_forward_kernel<6><<<grid, kPooledThreads, 0, (cudaStream_t)stream>>>(
             means, stds, B, (int)M, contract, reinterpret_cast<const float4*>(embeddings), pl, features, coord);
@@ -130,7 +133,7 @@ extern "C" int ucnerf_pooled_encode_forward(const float* means, const float* std
 }
 
 extern "C" int ucnerf_pooled_encode_backward(const float* grad_features, const float* means, const float* stds, uint32_t B,
-                                             uint32_t M, int contract, const int32_t* offsets_host,
+                                             uint32_t M, int flags, const int32_t* offsets_host,
                                              const int32_t* grid_sizes_host, uint32_t L, uint32_t C, float S, uint32_t H,
                                              float* grad_embeddings, void* stream) {
     UC_REQUIRE(C == 4, "pooled_encode: level_dim must be 4");
@@ -140,12 +143,18 @@ extern "C" int ucnerf_pooled_encode_backward(const float* grad_features, const f
     PooledLevels pl;
     if (int e = make_levels(pl, offsets_host, grid_sizes_host, L, S, H)) return e;
     const dim3 grid(div_up(B, (uint32_t)kPooledThreads), L, 1);
-    if (M == 6)
-        pooled_backward_kernel<6><<<grid, kPooledThreads, 0, (cudaStream_t)stream>>>(
-            grad_features, means, stds, B, (int)M, contract, pl, reinterpret_cast<float4*>(grad_embeddings));
+    const int contract = flags & UCNERF_POOLED_CONTRACT;
+    const bool runs = (flags & UCNERF_POOLED_MERGE_RUNS) != 0;
+    float4* ge = reinterpret_cast<float4*>(grad_embeddings);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M == 6 && runs)
+        pooled_backward_kernel<6, true><<<grid, kPooledThreads, 0, st>>>(grad_features, means, stds, B, (int)M, contract, pl, ge);
+    else if (M == 6)
+        pooled_backward_kernel<6, false><<<grid, kPooledThreads, 0, st>>>(grad_features, means, stds, B, (int)M, contract, pl, ge);
+    else if (runs)
+        pooled_backward_kernel<0, true><<<grid, kPooledThreads, 0, st>>>(grad_features, means, stds, B, (int)M, contract, pl, ge);
     else
-        pooled_backward_kernel<0><<<grid, kPooledThreads, 0, (cudaStream_t)stream>>>(
-            grad_features, means, stds, B, (int)M, contract, pl, reinterpret_cast<float4*>(grad_embeddings));
+        pooled_backward_kernel<0, false><<<grid, kPooledThreads, 0, st>>>(grad_features, means, stds, B, (int)M, contract, pl, ge);
     UC_LAUNCH_CHECK();
     return 0;
 }

@@ -42,7 +42,7 @@ def _check(cond, msg):
 class _pooled_encode(Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, means, stds, embeddings, offsets_h, grid_sizes_h, S, H, contract):
+    def forward(ctx, means, stds, embeddings, offsets_h, grid_sizes_h, S, H, contract, merge_runs):
         _check(means.device.type == "cuda" and embeddings.device.type == "cuda", "pooled_encode: tensors must be CUDA tensors")
         _check(embeddings.dtype == torch.float32 and embeddings.is_contiguous(), "pooled_encode: embeddings must be contiguous fp32")
         _check(embeddings.shape[1] == 4, "pooled_encode: level_dim must be 4")
@@ -63,7 +63,7 @@ class _pooled_encode(Function):
                                                   torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "pooled_encode_forward")
         ctx.save_for_backward(m2, s2, embeddings)
-        ctx.meta = (offsets_h, grid_sizes_h, S, H, contract, B, M, L)
+        ctx.meta = (offsets_h, grid_sizes_h, S, H, contract, merge_runs, B, M, L)
         feats, coord = feats.view(*lead, L * 4), coord.view(*lead, 3)
         ctx.mark_non_differentiable(coord)
         return feats, coord
@@ -72,21 +72,24 @@ class _pooled_encode(Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_feats, _grad_coord):
         m2, s2, embeddings = ctx.saved_tensors
-        offsets_h, grid_sizes_h, S, H, contract, B, M, L = ctx.meta
+        offsets_h, grid_sizes_h, S, H, contract, merge_runs, B, M, L = ctx.meta
         g = grad_feats.reshape(B, L * 4).contiguous().float()
         grad_emb = torch.zeros_like(embeddings)
         lib = _lib.load()
         with torch.cuda.device(g.device):
-            rc = lib.ucnerf_pooled_encode_backward(g.data_ptr(), m2.data_ptr(), s2.data_ptr(), B, M, int(contract),
+            flags = int(contract) | (2 if merge_runs else 0)      # UCNERF_POOLED_CONTRACT | UCNERF_POOLED_MERGE_RUNS
+            rc = lib.ucnerf_pooled_encode_backward(g.data_ptr(), m2.data_ptr(), s2.data_ptr(), B, M, flags,
                                                    offsets_h.ctypes.data, grid_sizes_h.ctypes.data, L, 4, float(S), int(H),
                                                    grad_emb.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "pooled_encode_backward")
-        return None, None, grad_emb, None, None, None, None, None
+        return None, None, grad_emb, None, None, None, None, None, None
 
 
-def pooled_encode(encoder, means, stds, contract=True):
+def pooled_encode(encoder, means, stds, contract=True, merge_runs=False):
     """`encoder`: a GridEncoder (this package's mirror or the reference's own class - only `embeddings`, `offsets`,
     `grid_sizes`, `per_level_scale`, `base_resolution` and the configuration attributes are read).
+    `merge_runs`: backward variant that sums the corner weights of consecutive points sharing a cell before the atomic
+    reductions (same gradient up to fp32 summation order; not yet measured on a GPU, hence off by default).
     Returns (features [..., L*C], coord [..., 3])."""
     _check(encoder.input_dim == 3 and encoder.level_dim == 4, "pooled_encode: input_dim 3 / level_dim 4 only")
     _check(getattr(encoder, "gridtype", "hash") == "hash" and not encoder.align_corners
@@ -94,4 +97,4 @@ def pooled_encode(encoder, means, stds, contract=True):
            "pooled_encode: hash grid, align_corners=False, linear interpolation only")
     offsets_h, grid_sizes_h = _host_layout(encoder)
     return _pooled_encode.apply(means, stds, encoder.embeddings, offsets_h, grid_sizes_h,
-                                np.log2(encoder.per_level_scale), encoder.base_resolution, bool(contract))
+                                np.log2(encoder.per_level_scale), encoder.base_resolution, bool(contract), bool(merge_runs))

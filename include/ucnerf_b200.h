@@ -113,6 +113,20 @@ int ucnerf_resample_intervals(const float* t_prev, const float* w_prev, uint32_t
                               float dilation, float anneal, float padding, int32_t S, const float* u, const float* jitter,
                               int32_t jitter_cols, float* out_sdist, void* stream);
 
+/* Differentiable alpha compositing for the training step (render.py:L155-174 compute_alpha_weights with
+ * opaque_background = False, and the acc / bg_w / rgb lines of volumetric_rendering, L202-205).  Device fp32:
+ * tdist [N, S+1] metric fenceposts (no gradient: sdist is detached, models.py:L203-204), density [N, S], rgbs [N, S, 3] or
+ * NULL (proposal levels), dirs [N, 3] (NOT unit norm), bg = the constant background intensity.
+ * forward  -> weights [N, S], rgb [N, 3], acc [N].
+ * backward: incoming g_weights [N, S] / g_rgb [N, 3] / g_acc [N] (each may be NULL = no gradient), the forward's
+ *           weights / acc -> d_density [N, S], d_rgbs [N, S, 3] (NULL allowed; ignored when rgbs is NULL). */
+int ucnerf_composite_train_forward(const float* tdist, const float* density, const float* rgbs, const float* dirs, uint32_t N,
+                                   int32_t S, float bg, float* weights, float* rgb, float* acc, void* stream);
+int ucnerf_composite_train_backward(const float* tdist, const float* density, const float* rgbs, const float* dirs,
+                                    const float* weights, const float* acc, const float* g_weights, const float* g_rgb,
+                                    const float* g_acc, uint32_t N, int32_t S, float bg, float* d_density, float* d_rgbs,
+                                    void* stream);
+
 /* ---- fused forward render (eval path, rand=False) ---- */
 
 /* One MLP's GridEncoder + density_layer (models.py:L425-441).  Pointers are device pointers to the

@@ -30,7 +30,7 @@ def harness():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "cpu_harness.so")
     src = os.path.join(ROOT, "tests", "cpu_harness.cpp")
-    hdrs = [os.path.join(ROOT, "ucnerf_b200", "csrc", f) for f in ("ray_algos.cuh", "common.cuh", "pooled_algos.cuh")]
+    hdrs = [os.path.join(ROOT, "ucnerf_b200", "csrc", f) for f in ("ray_algos.cuh", "common.cuh", "pooled_algos.cuh", "train_algos.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in [src] + hdrs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I/usr/local/cuda/include",
                                src, "-o", so])

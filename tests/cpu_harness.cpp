@@ -7,6 +7,7 @@
 #include <vector>
 #include "../ucnerf_b200/csrc/ray_algos.cuh"
 #include "../ucnerf_b200/csrc/pooled_algos.cuh"
+#include "../ucnerf_b200/csrc/train_algos.cuh"
 
 using namespace ucnerf;
 
@@ -199,6 +200,32 @@ extern "C" void h_pooled_backward(int B, int M, int flags, int L, const int32_t*
             if (flags & 2) pooled_level_backward_runs(lv, g2, means + (size_t)b * M * 3, stds + (size_t)b * M, M, contract, dF, HostAdd{grad_table});
             else pooled_level_backward(lv, g2, means + (size_t)b * M * 3, stds + (size_t)b * M, M, contract, dF, HostAdd{grad_table});
         }
+    }
+}
+
+// differentiable compositing (train_algos.cuh), the loops the CUDA kernels run one thread per ray
+extern "C" void h_composite_train_forward(int N, int S, const float* tdist, const float* density, const float* rgbs,
+                                          const float* dirs, float bg, float* weights, float* rgb, float* acc) {
+    for (int r = 0; r < N; ++r) {
+        const float dn = norm3(dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]);
+        float c[3], a;
+        composite_train_forward_ray(S, tdist + (size_t)r * (S + 1), density + (size_t)r * S,
+                                    rgbs ? rgbs + (size_t)r * S * 3 : nullptr, dn, bg, weights + (size_t)r * S, c, a);
+        rgb[3 * r] = c[0]; rgb[3 * r + 1] = c[1]; rgb[3 * r + 2] = c[2];
+        acc[r] = a;
+    }
+}
+extern "C" void h_composite_train_backward(int N, int S, const float* tdist, const float* density, const float* rgbs,
+                                           const float* dirs, float bg, const float* weights, const float* acc,
+                                           const float* g_w, const float* g_rgb, const float* g_acc, float* d_density,
+                                           float* d_rgbs) {
+    for (int r = 0; r < N; ++r) {
+        const float dn = norm3(dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]);
+        composite_train_backward_ray(S, tdist + (size_t)r * (S + 1), density + (size_t)r * S,
+                                     rgbs ? rgbs + (size_t)r * S * 3 : nullptr, dn, bg, weights + (size_t)r * S, acc[r],
+                                     g_w ? g_w + (size_t)r * S : nullptr, g_rgb ? g_rgb + 3 * r : nullptr,
+                                     g_acc ? g_acc + r : nullptr, d_density + (size_t)r * S,
+                                     (rgbs && d_rgbs) ? d_rgbs + (size_t)r * S * 3 : nullptr);
     }
 }
 

@@ -103,6 +103,8 @@ EXPORTS = [
     "ucnerf_pooled_encode_forward",
     "ucnerf_pooled_encode_backward",
     "ucnerf_resample_intervals",
+    "ucnerf_composite_train_forward",
+    "ucnerf_composite_train_backward",
 ]
 
 _lib = None
@@ -146,6 +148,8 @@ def load():
     lib.ucnerf_pooled_encode_forward.argtypes = [vp, vp, u32, u32, C.c_int, vp, vp, vp, u32, u32, C.c_float, u32, vp, vp, vp]
     lib.ucnerf_pooled_encode_backward.argtypes = [vp, vp, vp, u32, u32, C.c_int, vp, vp, u32, u32, C.c_float, u32, vp, vp]
     lib.ucnerf_resample_intervals.argtypes = [vp, vp, u32, i32, C.c_int, f32, f32, f32, i32, vp, vp, i32, vp, vp]
+    lib.ucnerf_composite_train_forward.argtypes = [vp, vp, vp, vp, u32, i32, f32, vp, vp, vp, vp]
+    lib.ucnerf_composite_train_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, i32, f32, vp, vp, vp]
     lib.ucnerf_sky_create.argtypes = [C.POINTER(SkyDesc), C.POINTER(vp)]
     lib.ucnerf_sky_destroy.argtypes = [vp]
     lib.ucnerf_sky_render.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_double, vp, vp]

@@ -48,3 +48,25 @@ def test_argument_validation_without_gpu(lib):
     assert rc != 0 and b"dtype" in lib.ucnerf_last_error()
     # empty batch is a no-op success
     assert lib.ucnerf_grid_encode_forward(None, None, None, None, 0, 3, 4, 1, 1.0, 16, None, 0, 0, 0, 0, None) == 0
+
+
+def test_training_ops_validate_arguments_without_gpu(lib):
+    """The training-step entry points reject bad shapes before any CUDA call; empty batches are no-op successes."""
+    import numpy as np
+    offs = np.array([0, 8, 16], np.int32)
+    gsz = np.array([17, 33], np.int32)
+    op, gp = offs.ctypes.data, gsz.ctypes.data
+    assert lib.ucnerf_pooled_encode_forward(None, None, 0, 6, 1, None, op, gp, 2, 4, 1.0, 16, None, None, None) == 0
+    assert lib.ucnerf_pooled_encode_forward(None, None, 0, 6, 1, None, op, gp, 2, 2, 1.0, 16, None, None, None) != 0
+    assert b"level_dim" in lib.ucnerf_last_error()
+    assert lib.ucnerf_pooled_encode_backward(None, None, None, 0, 9, 1, op, gp, 2, 4, 1.0, 16, None, None) != 0
+    assert b"multisample" in lib.ucnerf_last_error()
+    assert lib.ucnerf_pooled_encode_forward(None, None, 5, 6, 1, None, op, gp, 2, 4, 1.0, 16, None, None, None) != 0
+    assert b"null" in lib.ucnerf_last_error()
+    assert lib.ucnerf_resample_intervals(None, None, 0, 1, 0, 0.0, 1.0, 0.0, 32, None, None, 0, None, None) == 0
+    assert lib.ucnerf_resample_intervals(None, None, 4, 1, 0, 0.0, 1.0, 0.0, 1, None, None, 0, None, None) != 0
+    assert b"S >= 2" in lib.ucnerf_last_error()
+    assert lib.ucnerf_composite_train_forward(None, None, None, None, 0, 32, 1.0, None, None, None, None) == 0
+    assert lib.ucnerf_composite_train_forward(None, None, None, None, 3, 0, 1.0, None, None, None, None) != 0
+    assert lib.ucnerf_composite_train_backward(None, None, None, None, None, None, None, None, None, 3, 8, 1.0, None, None, None) != 0
+    assert b"null" in lib.ucnerf_last_error()

@@ -127,6 +127,14 @@ int ucnerf_composite_train_backward(const float* tdist, const float* density, co
                                     const float* g_acc, uint32_t N, int32_t S, float bg, float* d_density, float* d_rgbs,
                                     void* stream);
 
+/* Stand-alone render.cast_rays (internal/render.py:L94-152) for the training step.  Device fp32: tdist [N, S+1] metric
+ * fenceposts, origins / directions / cam_dirs [N,3], radii [N], rand_vec [N,3] = the torch.randn_like(cam_dirs) draw
+ * of L140; rot01 / flip01 [N,S] = the two torch.rand_like draws of rand=True (L121-122: rotation, flip mask), both NULL
+ * for the deterministic pattern (L125-131).  Outputs means [N,S,6,3], stds [N,S,6], ts [N,S,6] (ts may be NULL). */
+int ucnerf_cast_rays(const float* tdist, const float* origins, const float* directions, const float* cam_dirs,
+                     const float* radii, const float* rand_vec, const float* rot01, const float* flip01, uint32_t n_rays,
+                     int32_t S, float std_scale, float* means, float* stds, float* ts, void* stream);
+
 /* ---- fused forward render (eval path, rand=False) ---- */
 
 /* One MLP's GridEncoder + density_layer (models.py:L425-441).  Pointers are device pointers to the

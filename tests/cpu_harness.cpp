@@ -229,6 +229,23 @@ extern "C" void h_composite_train_backward(int N, int S, const float* tdist, con
     }
 }
 
+// render.cast_rays (train_algos.cuh::cast_interval): means [N,S,6,3], stds [N,S,6], ts [N,S,6]; rot01 / flip01 NULL = rand=False
+extern "C" void h_cast_rays(int N, int S, const float* tdist, const float* origins, const float* directions,
+                            const float* cam_dirs, const float* radii, const float* rand_vec, const float* rot01,
+                            const float* flip01, float std_scale, float* means, float* stds, float* ts) {
+    ConeTable ct;
+    make_cone_table(ct);
+    for (int r = 0; r < N; ++r) {
+        RayGeom rg;
+        make_ray_geom(rg, origins + 3 * r, directions + 3 * r, cam_dirs + 3 * r, rand_vec + 3 * r, radii[r], 0.f, 1.f);
+        for (int s = 0; s < S; ++s) {
+            const size_t q = (size_t)r * S + s;
+            cast_interval(rg, tdist[(size_t)r * (S + 1) + s], tdist[(size_t)r * (S + 1) + s + 1], ct, s, rot01 != nullptr,
+                          rot01 ? rot01[q] : 0.f, flip01 ? flip01[q] : 1.f, std_scale, means + q * 18, stds + q * 6, ts + q * 6);
+        }
+    }
+}
+
 // debug variant: also returns the scratch arrays of the last ray processed (T, W(=probabilities), CW, C)
 extern "C" void h_resample_debug(int n_prev, const float* t_prev, const float* w_prev, int dilate, float dilation,
                                  float anneal, float padding, int S, const float* u, float* out, float* T, float* W,

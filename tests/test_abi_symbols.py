@@ -68,5 +68,7 @@ def test_training_ops_validate_arguments_without_gpu(lib):
     assert b"S >= 2" in lib.ucnerf_last_error()
     assert lib.ucnerf_composite_train_forward(None, None, None, None, 0, 32, 1.0, None, None, None, None) == 0
     assert lib.ucnerf_composite_train_forward(None, None, None, None, 3, 0, 1.0, None, None, None, None) != 0
+    assert lib.ucnerf_cast_rays(None, None, None, None, None, None, None, None, 0, 8, 0.5, None, None, None, None) == 0
+    assert lib.ucnerf_cast_rays(None, None, None, None, None, None, None, None, 2, 8, 0.5, None, None, None, None) != 0
     assert lib.ucnerf_composite_train_backward(None, None, None, None, None, None, None, None, None, 3, 8, 1.0, None, None, None) != 0
     assert b"null" in lib.ucnerf_last_error()

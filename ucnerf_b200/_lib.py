@@ -105,6 +105,7 @@ EXPORTS = [
     "ucnerf_resample_intervals",
     "ucnerf_composite_train_forward",
     "ucnerf_composite_train_backward",
+    "ucnerf_cast_rays",
 ]
 
 _lib = None
@@ -150,6 +151,7 @@ def load():
     lib.ucnerf_resample_intervals.argtypes = [vp, vp, u32, i32, C.c_int, f32, f32, f32, i32, vp, vp, i32, vp, vp]
     lib.ucnerf_composite_train_forward.argtypes = [vp, vp, vp, vp, u32, i32, f32, vp, vp, vp, vp]
     lib.ucnerf_composite_train_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, i32, f32, vp, vp, vp]
+    lib.ucnerf_cast_rays.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32, i32, f32, vp, vp, vp, vp]
     lib.ucnerf_sky_create.argtypes = [C.POINTER(SkyDesc), C.POINTER(vp)]
     lib.ucnerf_sky_destroy.argtypes = [vp]
     lib.ucnerf_sky_render.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, C.c_double, vp, vp]

@@ -73,3 +73,51 @@ UC_HD void composite_train_backward_ray(int S, const float* t, const float* dens
 }
 
 }  // namespace ucnerf
+
+namespace ucnerf {
+
+// render.cast_rays for one multisample point of one interval, BEFORE any warp / contraction: world-space mean, std and
+// the point's distance t (render.py:L108-148).  `cosv`, `sinv`: cos / sin of the point's angle in the cone cross
+// section; the lateral offsets and the std are divided by sqrt(2) with an IEEE division exactly as the reference does
+// (the eval kernel's cone_point multiplies by the reciprocal instead and fuses the contraction).
+UC_HD void cast_point(const RayGeom& rg, const ConeInterval& ci, float tcoef, float cosv, float sinv, float std_scale,
+                      float (&mean)[3], float& std, float& t_out) {
+    const float t = fa(ci.t0, fm(ci.tdA, fa(ci.B, fm(tcoef, ci.Cq))));
+    const float rt = fm(rg.radius, t);
+    const float px = fd(fm(rt, cosv), 1.41421356237f);
+    const float py = fd(fm(rt, sinv), 1.41421356237f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        mean[i] = fa(fa(fa(fm(px, rg.e1[i]), fm(py, rg.e2[i])), fm(t, rg.d[i])), rg.o[i]);
+    std = fd(fm(fm(std_scale, rg.radius), t), 1.41421356237f);
+    t_out = t;
+}
+
+// The six points of interval s of one ray.  rand = false: the deterministic pattern (30-degree rotation and flip of every
+// other interval, render.py:L125-131, cos / sin from the torch-pinned table).  rand = true (training, L119-124):
+// rot01, flip01 = the ray's uniform draws for this interval: angle_j = pi/3 k_j + 2 pi rot01, kept if flip01 > 0.5, else
+// 5 pi / 3 - angle_j.  means [6*3], stds [6], ts [6].
+UC_HD void cast_interval(const RayGeom& rg, float t0, float t1, const ConeTable& ct, int s, bool rand, float rot01,
+                         float flip01, float std_scale, float* means, float* stds, float* ts) {
+    const ConeInterval ci = make_cone_interval(t0, t1);
+    const float kk[6] = {0.f, 2.f, 4.f, 3.f, 5.f, 1.f};
+    for (int j = 0; j < 6; ++j) {
+        float cv, sv;
+        if (rand) {
+            float deg = fa(fm(1.0471975511965976f, kk[j]), fm(6.283185307179586f, rot01));
+            if (!(flip01 > 0.5f)) deg = fs(5.235987755982989f, deg);
+            cv = cosf(deg);
+            sv = sinf(deg);
+        } else {
+            cv = ct.cosv[s & 1][j];
+            sv = ct.sinv[s & 1][j];
+        }
+        float m[3], sd, t;
+        cast_point(rg, ci, ct.tcoef[j], cv, sv, std_scale, m, sd, t);
+        means[3 * j] = m[0]; means[3 * j + 1] = m[1]; means[3 * j + 2] = m[2];
+        stds[j] = sd;
+        ts[j] = t;
+    }
+}
+
+}  // namespace ucnerf

@@ -70,3 +70,43 @@ class _composite(Function):
 def composite(density, rgbs, tdist, dirs, bg=1.0):
     """density [N,S], rgbs [N,S,3] or None, tdist [N,S+1], dirs [N,3] -> (weights [N,S], rgb [N,3], acc [N])."""
     return _composite.apply(density, rgbs, tdist, dirs, bg)
+
+
+@torch.no_grad()
+def cast_rays(tdist, origins, directions, cam_dirs, radii, rand=True, n=7, m=3, std_scale=0.5, generator=None, draws=None,
+              **kwargs):
+    """Drop-in for the reference's `render.cast_rays` (internal/render.py:L94-152, same positional arguments and return
+    values): tdist [N,S+1] + rays -> (means [N,S,6,3], stds [N,S,6], t [N,S,6]) through `ucnerf_cast_rays`, one kernel.
+    The random numbers are drawn with torch on the device in the reference's order - flip mask (L121), rotation (L122),
+    `rand_vec` (L140) - so a seeded generator reproduces the reference's stream; `draws = (flip01, rot01, rand_vec)`
+    supplies them explicitly.  No gradient flows (tdist is detached by the caller, models.py:L203-204)."""
+    if tdist.device.type != "cuda":
+        raise RuntimeError("cast_rays: tensors must be CUDA tensors (no CPU path)")
+    if tdist.dim() != 2:
+        raise RuntimeError("cast_rays: expected tdist [N, S+1] (flatten the leading dimensions first)")
+    N, S = tdist.shape[0], tdist.shape[1] - 1
+    dev = tdist.device
+    f = lambda x, cols: x.detach().reshape(N, cols).contiguous().float()
+    t = tdist.detach().contiguous().float()
+    o, d, c, r = f(origins, 3), f(directions, 3), f(cam_dirs, 3), f(radii, 1)
+    if draws is not None:
+        flip01, rot01, rand_vec = draws
+    else:
+        flip01 = torch.rand((N, S), device=dev, generator=generator) if rand else None
+        rot01 = torch.rand((N, S), device=dev, generator=generator) if rand else None
+        rand_vec = torch.randn((N, 3), device=dev, generator=generator)
+    if rand and (flip01 is None or rot01 is None):
+        raise RuntimeError("cast_rays: rand=True needs the flip and rotation draws")
+    flip01 = f(flip01, S) if rand else None
+    rot01 = f(rot01, S) if rand else None
+    rand_vec = f(rand_vec, 3)
+    means = torch.empty((N, S, 6, 3), device=dev, dtype=torch.float32)
+    stds = torch.empty((N, S, 6), device=dev, dtype=torch.float32)
+    ts = torch.empty((N, S, 6), device=dev, dtype=torch.float32)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.ucnerf_cast_rays(t.data_ptr(), o.data_ptr(), d.data_ptr(), c.data_ptr(), r.data_ptr(), rand_vec.data_ptr(),
+                                  _ptr(rot01), _ptr(flip01), N, S, float(std_scale), means.data_ptr(), stds.data_ptr(),
+                                  ts.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "cast_rays")
+    return means, stds, ts

@@ -5,7 +5,8 @@ Public surface (mirrors the reference):
     ucnerf_b200.render.render_image          <- nerf/internal/models.py::render_image
     ucnerf_b200.render.HotPathModel.forward  <- nerf/internal/models.py::Model.forward (eval path)
     ucnerf_b200/dropin/_gridencoder.py       <- the compiled `_gridencoder` extension module
-Ops for the reference's training step (INTEGRATION.md seams 5-9):
+Ops for the reference's training step (INTEGRATION.md seams 5-10):
+    ucnerf_b200.train_forward.level_loop           <- the level loop of Model.forward(rand=True) (models.py:L126-311)
     ucnerf_b200.gridencoder.pooled.pooled_encode   <- MLP.predict_density front end (models.py:L485-496), fwd + bwd
     ucnerf_b200.stepfun.resample_level             <- max_dilate_weights + sample_intervals (models.py:L156-205)
     ucnerf_b200.render_train.cast_rays             <- render.cast_rays (render.py:L94-152), rand on / off

@@ -328,7 +328,8 @@ class HotPathModel:
         """`Model.forward` contract for the eval path (internal/models.py:L97-365, heads excluded):
         returns (renderings, ray_history), one entry per sampling level."""
         if rand:
-            raise NotImplementedError("the fused path implements the deterministic eval path (rand=False)")
+            raise NotImplementedError("the fused path implements the deterministic eval path (rand=False); for the training "
+                                      "step use ucnerf_b200.train_forward.level_loop on the torch model")
         lead = batch['origins'].shape[:-1]
         flat = {k: batch[k].reshape(-1, batch[k].shape[-1]) for k in _RAY_KEYS}
         if rand_vec is None and batch.get('rand_vec') is not None:

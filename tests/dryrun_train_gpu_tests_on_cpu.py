@@ -114,6 +114,6 @@ def run_module(name, skip=()):
 
 for m, skip in (('test_train_resample', ()), ('test_train_render_composite', ()), ('test_train_sample_cast_rays', ()),
                 ('test_train_pooled_encode', ('test_cuda_equals_the_unfused_gridencoder_chain_and_errors', 'test_cuda_full_training_size_properties')),
-                ('test_train_zz_level_chain', ()), ('test_train_zzz_forward', ())):
+                ('test_train_zz_level_chain', ()), ('test_train_zzz_forward', ('test_mirror_model_forward_dispatch_eval_is_the_fused_path_and_follows_weight_updates',))):
     print(m); run_module(m, skip)
 print("ALL DRY RUNS OK")

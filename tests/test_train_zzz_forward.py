@@ -1,8 +1,8 @@
 """`ucnerf_b200.train_forward.level_loop` - Model.forward's level loop for the training step through the native ops -
 against vectors from the REFERENCE's own Model.forward(rand=True) in train() mode with autograd on CPU
 (oracle/make_train_forward_golden.py: draws patched in, loss over rgb / weights / acc / hash decay of both levels,
-gradients of every parameter).  The model handed to level_loop is a mirror with the reference's attribute and
-parameter names (the reference itself does not travel to the GPU box).  Sorted last: it runs every training op."""
+gradients of every parameter).  The model handed to level_loop is the product's mirror of the reference classes
+(ucnerf_b200/models.py: same attribute and parameter names; the reference itself does not travel to the GPU box).  Sorted last: it runs every training op."""
 import types
 
 import numpy as np
@@ -14,42 +14,15 @@ from conftest import load_golden
 from oracle import cases
 
 
-class MirrorMLP(nn.Module):
-    """Attribute / parameter names of the reference's MLP (models.py:L367-483) under configs/waymo.gin."""
-    deg_view, net_depth_viewdirs, skip_layer_dir = 4, 2, 0
-    density_bias, density_noise, bottleneck_noise = -1., 0., 0.
-    rgb_premultiplier, rgb_bias, rgb_padding = 1., 0., 0.001
-    disable_density_normals, warp_fn, num_glo_features, scale_featurization = True, 'contract', 0, False
-
-    def __init__(self, gs, disable_rgb, bottleneck_width=256, width=256):
-        super().__init__()
-        from ucnerf_b200.gridencoder import GridEncoder
-        self.disable_rgb, self.bottleneck_width = disable_rgb, bottleneck_width
-        self.encoder = GridEncoder(3, gs.num_levels, gs.level_dim, base_resolution=gs.base_resolution,
-                                   desired_resolution=gs.desired_resolution, log2_hashmap_size=gs.log2_hashmap_size)
-        self.density_layer = nn.Sequential(nn.Linear(self.encoder.output_dim, 64), nn.ReLU(),
-                                           nn.Linear(64, 1 if disable_rgb else bottleneck_width))
-        if not disable_rgb:
-            d_in = bottleneck_width + 27
-            self.lin_second_stage_0 = nn.Linear(d_in, width)
-            self.lin_second_stage_1 = nn.Linear(width + d_in, width)
-            self.rgb_layer = nn.Linear(width, 3)
-
-
-class MirrorModel(nn.Module):
-    """Attribute names of the reference's Model (models.py:L28-55)."""
-    bg_intensity_range, anneal_slope, stop_level_grad, use_viewdirs, raydist_fn = (1., 1.), 10, True, True, None
-    single_jitter, num_glo_features, near_anneal_rate, single_mlp, distinct_prop = True, 0, None, False, True
-    resample_padding, opaque_background, std_scale, learned_exposure_scaling = 0.0, False, 0.5, False
-
-    def __init__(self, cfg):
-        super().__init__()
-        self.num_levels, self.num_prop_samples, self.num_nerf_samples = cfg.num_levels, cfg.num_prop_samples, cfg.num_nerf_samples
-        self.dilation_multiplier, self.dilation_bias = cfg.dilation_multiplier, cfg.dilation_bias
-        self.config = types.SimpleNamespace(brightness_correction=False, model_sky=False)
-        for i, gs in enumerate(cfg.prop_grids):
-            self.register_module(f"prop_mlp_{i}", MirrorMLP(gs, True))
-        self.nerf_mlp = MirrorMLP(cfg.nerf_grid, False, cfg.bottleneck_width, cfg.net_width_viewdirs)
+def make_model(cfg):
+    """The product's mirror of the reference Model under configs/waymo.gin (ucnerf_b200/models.py)."""
+    from ucnerf_b200.models import Model
+    return Model(config=types.SimpleNamespace(brightness_correction=False, model_sky=False, vis_num_rays=16),
+                 num_levels=cfg.num_levels, num_prop_samples=cfg.num_prop_samples, num_nerf_samples=cfg.num_nerf_samples,
+                 prop_desired_grid_size=[gs.desired_resolution for gs in cfg.prop_grids],
+                 dilation_multiplier=cfg.dilation_multiplier, dilation_bias=cfg.dilation_bias,
+                 nerf_mlp_kwargs=dict(grid_disired_resolution=cfg.nerf_grid.desired_resolution,
+                                      bottleneck_width=cfg.bottleneck_width, net_width_viewdirs=cfg.net_width_viewdirs))
 
 
 def loss_fn(renderings, ray_history, target, Gs):
@@ -67,6 +40,27 @@ def projections(g, seed):
         R = torch.randn(g.shape, generator=gen, dtype=torch.float64)
         out.append(float((g.double().cpu() * R).sum()))
     return np.array(out + [float(g.double().abs().sum())])
+
+
+def test_mirror_model_has_the_reference_state_dict_and_rejects_what_it_cannot_run():
+    """CPU: parameter / buffer names and shapes of ucnerf_b200.models.Model == the reference's state_dict (the golden
+    parameter set is keyed by the reference's names, oracle/ref_shim.py loads the same dict into the real Model)."""
+    from ucnerf_b200.models import MLP, Model
+    cfg, params, _ = cases.make_case("waymo", 2)
+    model = make_model(cfg)
+    sd = model.state_dict()
+    assert set(sd) - set(params) == {k for k in sd if k.endswith(".idx")}        # level-id buffer, not in the parameter set
+    assert set(params) <= set(sd)
+    for k, v in params.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    missing, unexpected = model.load_state_dict(params, strict=False)
+    assert not unexpected and all(k.endswith(".idx") for k in missing)
+    with pytest.raises(TypeError):
+        Model(num_levles=2)
+    with pytest.raises(NotImplementedError):
+        MLP(disable_density_normals=False)
+    with pytest.raises(NotImplementedError):
+        Model(single_mlp=True)
 
 
 def test_gradient_scaler_equals_train_utils_formula():
@@ -100,7 +94,7 @@ def test_level_loop_matches_the_reference_training_forward_and_backward():
     from ucnerf_b200.train_forward import level_loop
     g = load_golden("train_forward")
     cfg, params, batch = cases.make_case("waymo", g["target"].shape[0])
-    model = MirrorModel(cfg)
+    model = make_model(cfg)
     missing, unexpected = model.load_state_dict(params, strict=False)
     assert not unexpected and all(k.endswith(".idx") for k in missing), (missing, unexpected)
     model = model.cuda().train()
@@ -108,6 +102,7 @@ def test_level_loop_matches_the_reference_training_forward_and_backward():
     draws = [{k: torch.from_numpy(g[f"draw{l}_{k}"]).cuda() for k in ("jitter01", "flip01", "rot01", "rand_vec")}
              for l in range(cfg.num_levels)]
     renderings, ray_history = level_loop(model, True, b, float(g["train_frac"]), compute_extras=False, draws=draws)
+    assert model.training
     target = torch.from_numpy(g["target"]).cuda()
     Gs = [torch.from_numpy(g[f"G{l}"]).cuda() for l in range(cfg.num_levels)]
     loss = loss_fn(renderings, ray_history, target, Gs)
@@ -141,3 +136,26 @@ def test_level_loop_matches_the_reference_training_forward_and_backward():
             assert np.abs(got[:3] - ref[:3]).max() <= 0.05 * max(np.abs(ref[:3]).max(), scale), (name, got, ref)
             checked += 1
     assert checked == len(list(model.named_parameters()))
+
+
+@pytest.mark.gpu
+def test_mirror_model_forward_dispatch_eval_is_the_fused_path_and_follows_weight_updates():
+    """Model.forward: rand / training -> level_loop, eval -> the fused render path (== a HotPathModel built from the same
+    state_dict), refreshed when the parameters change in place (an optimiser step)."""
+    from ucnerf_b200.render import HotPathModel
+    cfg, params, batch = cases.make_case("waymo", 96)
+    model = make_model(cfg)
+    model.load_state_dict(params, strict=False)
+    model = model.cuda().eval()
+    b = {k: v.cuda() for k, v in batch.items()}
+    r1, h1 = model(False, b, 1.0, True)
+    ref = HotPathModel.from_reference_model(model, model.config)
+    r2, _ = ref.forward(False, b, 1.0, True)
+    assert torch.equal(r1[-1]["rgb"], r2[-1]["rgb"]) and torch.equal(r1[-1]["depth"], r2[-1]["depth"])
+    with torch.no_grad():
+        model.nerf_mlp.rgb_layer.bias.add_(0.5)
+    r3, _ = model(False, b, 1.0, True)
+    assert float((r3[-1]["rgb"] - r1[-1]["rgb"]).abs().max()) > 1e-3
+    model.train()
+    r4, h4 = model(True, {k: v for k, v in b.items() if k != "rand_vec"}, 0.5, False)
+    assert r4[-1]["rgb"].requires_grad and h4[0]["weights"].shape == (96, cfg.num_prop_samples)

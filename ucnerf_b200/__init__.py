@@ -4,6 +4,8 @@ Public surface (mirrors the reference):
     ucnerf_b200.gridencoder.GridEncoder      <- nerf/gridencoder/grid.py::GridEncoder
     ucnerf_b200.render.render_image          <- nerf/internal/models.py::render_image
     ucnerf_b200.render.HotPathModel.forward  <- nerf/internal/models.py::Model.forward (eval path)
+    ucnerf_b200.models.Model / NerfMLP / PropMLP <- the reference classes (same attributes / parameter names; forward
+                                                dispatches training -> train_forward.level_loop, eval -> the fused path)
     ucnerf_b200/dropin/_gridencoder.py       <- the compiled `_gridencoder` extension module
 Ops for the reference's training step (INTEGRATION.md seams 5-10):
     ucnerf_b200.train_forward.level_loop           <- the level loop of Model.forward(rand=True) (models.py:L126-311)

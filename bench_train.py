@@ -1,0 +1,193 @@
+#!/usr/bin/env python
+"""Secondary benchmark (not the driver contract): one optimisation step of the reference's training loop through the
+native ops - BASELINE.json configs[4] ("train.py one optimisation step (forward+backward through gridencoder/MLP)
+65536-ray batch, 8xB200"), i.e. 8,192 rays per GPU with the waymo.gin shapes (128 proposal + 32 NeRF samples):
+
+    forward   ucnerf_b200.models.Model(rand=True) = train_forward.level_loop: native resampling, cast_rays, pooled
+              hash-grid encode and compositing around the model's nn.Linear layers (cuBLAS)
+    loss      Charbonnier data loss on both levels (train_utils.compute_data_loss, data_loss_type='charb') + a
+              weights-dependent term standing in for the interlevel / distortion losses (they are the reference's own
+              Python and not part of this package)
+    backward  autograd through the native backward kernels
+    exchange  N > 1: all-reduce of the gradients (what DDP does for the reference)
+    step      torch.optim.Adam for the nn.Linear layers + the fused hash-decay + Adam + zero_grad kernel for the tables
+
+    python bench_train.py [--steps 10 --warmup 3 --rays 8192]            # 1 GPU
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 bench_train.py --gpus 8
+
+One JSON line from rank 0: rays/s over all ranks, ms per step (CUDA events, max over ranks) and the per-phase times."""
+import argparse
+import json
+import os
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import torch
+
+
+def build_model(dev):
+    from ucnerf_b200 import synthetic
+    from ucnerf_b200.models import Model
+    wl = synthetic.WORKLOADS["eval_800x600_waymo_gin"]
+    model = Model(config=types.SimpleNamespace(brightness_correction=False, model_sky=False, vis_num_rays=16),
+                  num_levels=2, num_prop_samples=wl.num_prop_samples, num_nerf_samples=wl.num_nerf_samples,
+                  prop_desired_grid_size=list(wl.prop_desired),
+                  nerf_mlp_kwargs=dict(grid_disired_resolution=wl.nerf_desired, bottleneck_width=wl.bottleneck_width,
+                                       net_width_viewdirs=wl.net_width_viewdirs,
+                                       grid_log2_hashmap_size=wl.log2_hashmap_size),
+                  prop_mlp_kwargs=dict(grid_log2_hashmap_size=wl.log2_hashmap_size))
+    sd = synthetic.synthetic_state_dict(wl, seed=0)            # same weights on every rank (replicas)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith(".idx") for k in missing), (missing, unexpected)
+    return model.to(dev).train(), wl
+
+
+def make_batch(n_rays, seed, dev):
+    from ucnerf_b200 import synthetic
+    height = 1 << (max(n_rays, 1).bit_length() - 1) // 2          # 8,192 rays -> a 64 x 128 pixel patch
+    rays = synthetic.pinhole_rays(height, max(n_rays // height, 1), seed=seed)
+    n = rays["origins"].shape[0]
+    g = torch.Generator().manual_seed(seed)
+    batch = {k: v.to(dev) for k, v in rays.items() if k != "rand_vec"}
+    batch["rgb"] = torch.rand((n, 3), generator=g).to(dev)
+    batch["lossmult"] = torch.ones((n, 1), device=dev)
+    return batch, n
+
+
+def compute_loss(batch, renderings, ray_history, charb_padding=0.001, coarse_mult=0.0, interlevel_like=0.01):
+    """train_utils.compute_data_loss (L171-230, data_loss_type='charb', data_coarse_loss_mult as given) + a term that puts
+    a gradient on the proposal weights like the interlevel loss does."""
+    lossmult = torch.broadcast_to(batch['lossmult'], batch['rgb'].shape)
+    denom = lossmult.sum()
+    data = []
+    for r in renderings:
+        resid_sq = (r['rgb'] - batch['rgb']) ** 2
+        data.append((lossmult * torch.sqrt(resid_sq + charb_padding ** 2)).sum() / denom)
+    loss = coarse_mult * sum(data[:-1]) + data[-1]
+    for h in ray_history[:-1]:
+        s = h['sdist']
+        loss = loss + interlevel_like * ((h['weights'] ** 2) / (s[..., 1:] - s[..., :-1]).clamp_min(1e-5)).mean()
+    return loss
+
+
+class Phases:
+    """CUDA-event timing of named phases, accumulated over the timed steps (no sync on the step path)."""
+
+    def __init__(self):
+        self.events = []
+
+    def mark(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.events.append((name, e))
+
+    def totals(self):
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self.events[:-1], self.events[1:]):
+            if n1 != "start":
+                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step (config 5: 65,536 / 8)")
+    a = ap.parse_args()
+    import torch.distributed as dist
+    from ucnerf_b200 import _lib
+    from ucnerf_b200.gridencoder.optim import GridAdam
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        sys.exit("bench_train.py needs a CUDA device: the training ops have no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model, wl = build_model(dev)
+    batch, n = make_batch(a.rays, seed=rank, dev=dev)
+    encoders = [m.encoder for m in (model.prop_mlp_0, model.nerf_mlp)]
+    table_ids = {id(e.embeddings) for e in encoders}
+    dense = [p for p in model.parameters() if id(p) not in table_ids]
+    opt = torch.optim.Adam(dense, lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    grid_opt = GridAdam(encoders, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, hash_decay_mult=0.1, zero_grad=True)
+    for e in encoders:                                   # the fused step zeroes these in place every step
+        e.embeddings.grad = torch.zeros_like(e.embeddings)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ph = Phases()
+
+    def step(timed):
+        from ucnerf_b200.train_forward import level_loop
+        if timed:
+            ph.mark("start")
+        opt.zero_grad(set_to_none=True)
+        renderings, ray_history = level_loop(model, True, batch, 0.5, compute_extras=False, hash_decay=False, generator=gen)
+        loss = compute_loss(batch, renderings, ray_history)
+        if timed:
+            ph.mark("forward")
+        loss.backward()
+        if timed:
+            ph.mark("backward")
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in dense])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in dense:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            for e in encoders:
+                dist.all_reduce(e.embeddings.grad)
+                e.embeddings.grad /= world
+            if timed:
+                ph.mark("exchange")
+        opt.step()
+        grid_opt.step()
+        if timed:
+            ph.mark("optimizer")
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step(False)
+    sync_all()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = step(True)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        phases = {k: v / a.steps for k, v in ph.totals().items()}
+        print(json.dumps({
+            "bench": "train_step (BASELINE.json configs[4])", "metric": "train_rays_per_sec",
+            "value": world * n * a.steps / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "rays_per_gpu_per_step": n, "samples_per_ray": wl.samples_per_ray,
+            "scaling": "weak", "dtype": "f32", "data": "synthetic", "phase_ms_per_step": phases,
+            "native_launches_per_step": (_lib.launch_count() - launches0) / a.steps, "final_loss": float(loss.detach()),
+            "note": "forward / backward through ucnerf_b200.train_forward.level_loop (native resample, cast_rays, pooled "
+                    "encode, composite; nn.Linear layers in cuBLAS fp32), torch Adam for the dense layers, fused "
+                    "hash-decay + Adam + zero_grad for the tables; N > 1 adds the gradient all-reduce DDP would do"}),
+              flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

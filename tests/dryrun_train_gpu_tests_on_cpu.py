@@ -9,7 +9,7 @@ signatures of include/ucnerf_b200.h and forward the raw host pointers to the ser
 algorithm templates (tests/cpu_harness.cpp).  It proves nothing about the CUDA instantiation itself - that is what the
 real `-m gpu` run is for - and it is not a CPU path of the product: the product raises without CUDA
 (tests/test_host_logic.py::test_renderer_refuses_to_run_without_cuda)."""
-import sys, types, ctypes, contextlib, importlib, re, os
+import sys, types, ctypes, contextlib, importlib, os
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, ROOT + '/tests')
@@ -80,9 +80,6 @@ import inspect
 def run_module(name, skip=()):
     mod = importlib.import_module(name)
     fixtures = {}
-    import conftest
-    for fname, fobj in vars(mod).items():
-        pass
     ok = 0
     for tname, fn in list(vars(mod).items()):
         if not tname.startswith('test_') or not callable(fn): continue

@@ -8,7 +8,6 @@ import types
 import numpy as np
 import pytest
 import torch
-import torch.nn as nn
 
 from conftest import load_golden
 from oracle import cases

@@ -18,7 +18,6 @@ the loop and keeps those lines (INTEGRATION.md seam 10).  Supported configuratio
 reflections / diffuse / tint / roughness / n_dot_v, `warp_fn='contract'`, `scale_featurization=False`,
 `opaque_background=False`, `compute_extras=False`; anything else raises NotImplementedError instead of diverging
 silently.  There is no CPU path."""
-import numpy as np
 import torch
 import torch.nn.functional as F
 

@@ -72,3 +72,27 @@ def test_training_ops_validate_arguments_without_gpu(lib):
     assert lib.ucnerf_cast_rays(None, None, None, None, None, None, None, None, 2, 8, 0.5, None, None, None, None) != 0
     assert lib.ucnerf_composite_train_backward(None, None, None, None, None, None, None, None, None, 3, 8, 1.0, None, None, None) != 0
     assert b"null" in lib.ucnerf_last_error()
+
+
+def test_ctypes_argtypes_match_the_header_declarations(lib):
+    """Every function declared in include/ucnerf_b200.h has ctypes argtypes of the same length and kind (pointer vs the
+    exact scalar type) in ucnerf_b200/_lib.py - the Python wrappers cannot drift from the C ABI unnoticed."""
+    txt = open(os.path.join(ROOT, "include", "ucnerf_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"//.*", "", txt)
+    decls = re.findall(r"\b(ucnerf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S)
+    scalar = {"uint32_t": ctypes.c_uint32, "int32_t": ctypes.c_int32, "int": ctypes.c_int, "float": ctypes.c_float,
+              "double": ctypes.c_double, "uint64_t": ctypes.c_uint64, "int64_t": ctypes.c_int64}
+    assert len(decls) >= 27
+    for name, params in decls:
+        plist = [q.strip() for q in params.split(",") if q.strip() and q.strip() != "void"]
+        at = getattr(lib, name).argtypes
+        if not plist:
+            continue
+        assert at is not None and len(at) == len(plist), (name, at, plist)
+        for i, (q, a) in enumerate(zip(plist, at)):
+            if "*" in q:
+                assert a in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(a, ctypes._Pointer), (name, i, q, a)
+            else:
+                base = re.sub(r"\bconst\b", "", q).split()[0]
+                assert scalar.get(base) is a, (name, i, q, a)

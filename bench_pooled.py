@@ -78,6 +78,11 @@ def main():
             f, _ = pooled_encode(enc, means, stds, merge_runs=True)
             f.backward(gf)
 
+        def fused_merge_ray():                  # ... and across 4 consecutive intervals of a ray
+            enc.embeddings.grad = None
+            f, _ = pooled_encode(enc, means, stds, merge_runs='ray')
+            f.backward(gf)
+
         def fused_fwd():
             with torch.no_grad():
                 pooled_encode(enc, means, stds)
@@ -95,10 +100,11 @@ def main():
         ms_f = timeit(fused, a.reps)
         ms_ff = timeit(fused_fwd, a.reps)
         ms_fm = timeit(fused_merge, a.reps)
+        ms_fr = timeit(fused_merge_ray, a.reps)
         ms_c = timeit(chain, max(3, a.reps // 2))
         alg = B * 6 * L * 8 * 16              # gathered (forward) or reduced (backward) table bytes per pass
         out["levels"][tag] = {"intervals": B, "grid_levels": L, "fused_fwd_bwd_ms": ms_f, "fused_fwd_ms": ms_ff,
-                              "fused_merge_runs_fwd_bwd_ms": ms_fm,
+                              "fused_merge_runs_fwd_bwd_ms": ms_fm, "fused_merge_ray_runs_fwd_bwd_ms": ms_fr,
                               "chain_fwd_bwd_ms": ms_c, "speedup": ms_c / ms_f,
                               "algorithmic_table_bytes_per_pass": alg,
                               "fwd_gather_gbs": alg / ms_ff / 1e6, "fwd_gather_frac_of_hbm_peak": alg / ms_ff / 1e6 / peak,

@@ -89,6 +89,7 @@ int ucnerf_grid_adam_step(float* embeddings, float* grad, float* exp_avg, float*
  * H = base_resolution as in ucnerf_grid_encode_forward.  C must be 4. */
 #define UCNERF_POOLED_CONTRACT 1     /* warp_fn = 'contract' and bound = 2 (models.py:L487-493) */
 #define UCNERF_POOLED_MERGE_RUNS 2   /* backward only: sum the corner weights of consecutive points that share a cell before reducing */
+#define UCNERF_POOLED_MERGE_RAY_RUNS 4   /* backward only: the same across 4 consecutive intervals (neighbouring samples of a ray) per thread; needs B % 4 == 0, else ignored */
 int ucnerf_pooled_encode_forward(const float* means, const float* stds, uint32_t B, uint32_t M, int flags,
                                  const float* embeddings, const int32_t* offsets_host, const int32_t* grid_sizes_host,
                                  uint32_t L, uint32_t C, float S, uint32_t H, float* features, float* coord, void* stream);

@@ -193,6 +193,12 @@ extern "C" void h_pooled_backward(int B, int M, int flags, int L, const int32_t*
         GridLevel lv;
         make_grid_level(lv, l, offsets[l], offsets[l + 1], S, H, grid_sizes[l]);
         const float g2 = (float)(int32_t)((int64_t)grid_sizes[l] * grid_sizes[l]);
+        if ((flags & 4) && B % 4 == 0) {      // ray-run variant: 4 consecutive intervals per (serial) thread
+            for (int b = 0; b < B; b += 4)
+                pooled_level_backward_ray_runs(lv, g2, means + (size_t)b * M * 3, stds + (size_t)b * M, M, 4, (flags & 1) != 0,
+                                               grad_features + (size_t)b * L * 4, L * 4, 4 * l, HostAdd{grad_table});
+            continue;
+        }
         for (int b = 0; b < B; ++b) {
             float dF[4];
             std::memcpy(dF, grad_features + ((size_t)b * L + l) * 4, 16);

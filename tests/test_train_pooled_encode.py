@@ -73,7 +73,7 @@ def _harness_run(harness, params, prefix, gs, means, stds, grad_feats, contract=
                              _fp(m), _fp(s), _fp(feats), _fp(coord))
     ge = np.zeros((emb.shape[0], 4), np.float64)
     gf = np.ascontiguousarray(grad_feats.reshape(B, L * 4), np.float32)
-    harness.h_pooled_backward(B, M, contract | (2 if merge_runs else 0), L, _fp(offs), _fp(gsz), ctypes.c_float(S), gs.base_resolution, _fp(gf),
+    harness.h_pooled_backward(B, M, contract | (4 if merge_runs == 'ray' else (2 if merge_runs else 0)), L, _fp(offs), _fp(gsz), ctypes.c_float(S), gs.base_resolution, _fp(gf),
                               _fp(m), _fp(s), _fp(ge))
     return feats, coord, ge
 
@@ -101,19 +101,21 @@ def test_run_merging_backward_gives_the_same_gradient_on_cpu(harness, case, tag)
     prefix, gsf = TAGS[tag]
     gs = gsf(cfg)
     _, _, ge0 = _harness_run(harness, params, prefix, gs, g["means"], g["stds"], g[f"{tag}_grad_features"])
-    _, _, ge1 = _harness_run(harness, params, prefix, gs, g["means"], g["stds"], g[f"{tag}_grad_features"], merge_runs=True)
-    ref = _dense_grad(g, tag, ge1.shape[0])
-    assert np.abs(ge1 - ge0).max() <= 2e-6 * np.abs(ref).max()
-    assert np.abs(ge1 - ref).max() <= 3e-6 * np.abs(ref).max()
-    assert np.array_equal(np.nonzero(np.abs(ge1).sum(-1))[0], g[f"{tag}_grad_rows"])
+    ref = _dense_grad(g, tag, ge0.shape[0])
+    for variant in (True, 'ray'):        # within an interval / across 4 consecutive intervals of a ray
+        _, _, ge1 = _harness_run(harness, params, prefix, gs, g["means"], g["stds"], g[f"{tag}_grad_features"], merge_runs=variant)
+        assert np.abs(ge1 - ge0).max() <= 2e-6 * np.abs(ref).max()
+        assert np.abs(ge1 - ref).max() <= 3e-6 * np.abs(ref).max()
+        assert np.array_equal(np.nonzero(np.abs(ge1).sum(-1))[0], g[f"{tag}_grad_rows"])
     # out-of-range points between in-range ones, no contraction, M = 3
     rng = np.random.default_rng(8)
     means = rng.uniform(-1.2, 1.2, (64, 3, 3)).astype(np.float32)
     stds = rng.uniform(1e-4, 5e-2, (64, 3)).astype(np.float32)
     gf = rng.standard_normal((64, gs.num_levels * 4)).astype(np.float32)
     _, _, a = _harness_run(harness, params, prefix, gs, means, stds, gf, contract=0)
-    _, _, b = _harness_run(harness, params, prefix, gs, means, stds, gf, contract=0, merge_runs=True)
-    assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max()
+    for variant in (True, 'ray'):
+        _, _, b = _harness_run(harness, params, prefix, gs, means, stds, gf, contract=0, merge_runs=variant)
+        assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max()
 
 
 def test_device_algorithm_edge_cases_on_cpu(harness, case):
@@ -257,13 +259,14 @@ def test_cuda_run_merging_backward_equals_the_plain_backward(case, M):
     stds = (5e-4 * t.expand(-1, M, 1)).reshape(B, M).contiguous().cuda()
     gf = torch.randn((B, gs.num_levels * 4), generator=g).cuda()
     grads = []
-    for merge in (False, True):
+    for merge in (False, True, 'ray'):
         enc.embeddings.grad = None
         feats, _ = pooled_encode(enc, means, stds, merge_runs=merge)
         feats.backward(gf)
         grads.append(enc.embeddings.grad.clone())
-    assert float((grads[0] - grads[1]).abs().max()) <= 1e-5 * float(grads[0].abs().max())
-    assert torch.equal(grads[0].abs().sum(-1) > 0, grads[1].abs().sum(-1) > 0)
+    for gm in grads[1:]:
+        assert float((grads[0] - gm).abs().max()) <= 1e-5 * float(grads[0].abs().max())
+        assert torch.equal(grads[0].abs().sum(-1) > 0, gm.abs().sum(-1) > 0)
 
 
 @pytest.mark.gpu

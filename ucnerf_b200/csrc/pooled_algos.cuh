@@ -155,6 +155,63 @@ UC_HD void pooled_level_backward_runs(const GridLevel& lv, float g2, const float
     }
 }
 
+// Run merging across K CONSECUTIVE intervals (neighbouring samples of one ray, K * M points ordered along the ray): on
+// the coarse levels a thread then issues one set of 8 reductions for the whole stretch instead of one per interval.
+// The intervals have different dF, so the 8 x 4 products are accumulated (not the 8 weights).  grad_features points at
+// the first interval's row; rows are `row_stride` floats apart; `level_off` = 4 * level.
+template <class Add>
+UC_HD void pooled_level_backward_ray_runs(const GridLevel& lv, float g2, const float* means, const float* stds, int M, int K,
+                                          bool contract, const float* grad_features, int row_stride, int level_off,
+                                          const Add& add) {
+    const float inv = 1.f / (float)M;
+    float a[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k][0] = a[k][1] = a[k][2] = a[k][3] = 0.f;
+    uint32_t cx = 0, cy = 0, cz = 0;
+    bool open = false;
+    for (int i = 0; i <= K; ++i) {
+        float dF[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i < K) {
+            const float* gp = grad_features + (size_t)i * row_stride + level_off;
+            dF[0] = gp[0]; dF[1] = gp[1]; dF[2] = gp[2]; dF[3] = gp[3];
+        }
+        const int npts = i < K ? M : 1;            // one extra pass closes the last run
+        for (int j = 0; j < npts; ++j) {
+            bool inside = false;
+            CellCoords c{};
+            float coef = 0.f;
+            if (i < K) {
+                float g[3], sigma, xh[3];
+                pooled_point(means + 3 * ((size_t)i * M + j), stds[(size_t)i * M + j], contract, g, sigma, xh);
+                inside = in_unit_cube(g);
+                if (inside) {
+                    c = cell_of(lv, g);
+                    coef = pooled_erf_weight(sigma, g2) * inv;
+                }
+            }
+            if (open && (i == K || (inside && (c.ix != cx || c.iy != cy || c.iz != cz)))) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t idx = level_index(lv, cx + (k & 1), cy + ((k >> 1) & 1), cz + ((k >> 2) & 1));
+                    add((size_t)lv.offset + idx, a[k][0], a[k][1], a[k][2], a[k][3]);
+                    a[k][0] = a[k][1] = a[k][2] = a[k][3] = 0.f;
+                }
+                open = false;
+            }
+            if (inside) {
+                cx = c.ix; cy = c.iy; cz = c.iz;
+                open = true;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float w = corner_weight(c, k) * coef;
+                    a[k][0] = fmaf(w, dF[0], a[k][0]); a[k][1] = fmaf(w, dF[1], a[k][1]);
+                    a[k][2] = fmaf(w, dF[2], a[k][2]); a[k][3] = fmaf(w, dF[3], a[k][3]);
+                }
+            }
+        }
+    }
+}
+
 // models.py:L512 means.mean(dim=-2) of the contracted means / 2
 UC_HD void pooled_coord(const float* means, const float* stds, int M, bool contract, float (&out)[3]) {
     float acc[3] = {0.f, 0.f, 0.f};

@@ -92,6 +92,21 @@ pooled_backward_kernel(const float* __restrict__ grad_features, const float* __r
     else pooled_level_backward(pl.lv[l], pl.g2[l], mj, sj, M, contract != 0, dF, TableRedAdd{grad_table});
 }
 
+// K consecutive intervals per thread with run merging across them (pooled_level_backward_ray_runs); B % K == 0
+template <int MT, int K>
+__global__ void __launch_bounds__(kPooledThreads)
+pooled_backward_ray_runs_kernel(const float* __restrict__ grad_features, const float* __restrict__ means,
+                                const float* __restrict__ stds, uint32_t groups, int M, int contract,
+                                const __grid_constant__ PooledLevels pl, float4* __restrict__ grad_table) {
+    const uint32_t gidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gidx >= groups) return;
+    const int l = blockIdx.y;
+    if (MT) M = MT;
+    const size_t b0 = (size_t)gidx * K;
+    pooled_level_backward_ray_runs(pl.lv[l], pl.g2[l], means + b0 * M * 3, stds + b0 * M, M, K, contract != 0,
+                                   grad_features + b0 * pl.num_levels * 4, pl.num_levels * 4, 4 * l, TableRedAdd{grad_table});
+}
+
 static int make_levels(PooledLevels& pl, const int32_t* offsets_host, const int32_t* grid_sizes_host, uint32_t L,
                        float S, uint32_t H) {
     UC_REQUIRE(offsets_host && grid_sizes_host, "pooled_encode: null offsets / grid_sizes");
@@ -147,6 +162,17 @@ extern "C" int ucnerf_pooled_encode_backward(const float* grad_features, const f
     const bool runs = (flags & UCNERF_POOLED_MERGE_RUNS) != 0;
     float4* ge = reinterpret_cast<float4*>(grad_embeddings);
     cudaStream_t st = (cudaStream_t)stream;
+    constexpr int kRayRun = 4;     // consecutive intervals per thread of the ray-run variant
+    if ((flags & UCNERF_POOLED_MERGE_RAY_RUNS) && B % kRayRun == 0) {
+        const uint32_t groups = B / kRayRun;
+        const dim3 g2(div_up(groups, (uint32_t)kPooledThreads), L, 1);
+        if (M == 6)
+            pooled_backward_ray_runs_kernel<6, kRayRun><<<g2, kPooledThreads, 0, st>>>(grad_features, means, stds, groups, (int)M, contract, pl, ge);
+        else
+            pooled_backward_ray_runs_kernel<0, kRayRun><<<g2, kPooledThreads, 0, st>>>(grad_features, means, stds, groups, (int)M, contract, pl, ge);
+        UC_LAUNCH_CHECK();
+        return 0;
+    }
     if (M == 6 && runs)
         pooled_backward_kernel<6, true><<<grid, kPooledThreads, 0, st>>>(grad_features, means, stds, B, (int)M, contract, pl, ge);
     else if (M == 6)

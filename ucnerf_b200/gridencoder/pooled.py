@@ -77,7 +77,8 @@ class _pooled_encode(Function):
         grad_emb = torch.zeros_like(embeddings)
         lib = _lib.load()
         with torch.cuda.device(g.device):
-            flags = int(contract) | (2 if merge_runs else 0)      # UCNERF_POOLED_CONTRACT | UCNERF_POOLED_MERGE_RUNS
+            # UCNERF_POOLED_CONTRACT | UCNERF_POOLED_MERGE_RUNS (merge_runs=True) | UCNERF_POOLED_MERGE_RAY_RUNS ('ray')
+            flags = int(contract) | (4 if merge_runs == 'ray' else (2 if merge_runs else 0))
             rc = lib.ucnerf_pooled_encode_backward(g.data_ptr(), m2.data_ptr(), s2.data_ptr(), B, M, flags,
                                                    offsets_h.ctypes.data, grid_sizes_h.ctypes.data, L, 4, float(S), int(H),
                                                    grad_emb.data_ptr(), torch.cuda.current_stream().cuda_stream)
@@ -88,8 +89,10 @@ class _pooled_encode(Function):
 def pooled_encode(encoder, means, stds, contract=True, merge_runs=False):
     """`encoder`: a GridEncoder (this package's mirror or the reference's own class - only `embeddings`, `offsets`,
     `grid_sizes`, `per_level_scale`, `base_resolution` and the configuration attributes are read).
-    `merge_runs`: backward variant that sums the corner weights of consecutive points sharing a cell before the atomic
-    reductions (same gradient up to fp32 summation order; not yet measured on a GPU, hence off by default).
+    `merge_runs`: backward variants that combine the contributions of consecutive points sharing a cell before the atomic
+    reductions - True: within an interval, 'ray': across 4 consecutive intervals (rows must be ordered ray by ray, sample
+    by sample, as render.cast_rays produces them) - same gradient up to fp32 summation order; not yet measured on a GPU,
+    hence off by default.
     Returns (features [..., L*C], coord [..., 3])."""
     _check(encoder.input_dim == 3 and encoder.level_dim == 4, "pooled_encode: input_dim 3 / level_dim 4 only")
     _check(getattr(encoder, "gridtype", "hash") == "hash" and not encoder.align_corners
@@ -97,4 +100,4 @@ def pooled_encode(encoder, means, stds, contract=True, merge_runs=False):
            "pooled_encode: hash grid, align_corners=False, linear interpolation only")
     offsets_h, grid_sizes_h = _host_layout(encoder)
     return _pooled_encode.apply(means, stds, encoder.embeddings, offsets_h, grid_sizes_h,
-                                np.log2(encoder.per_level_scale), encoder.base_resolution, bool(contract), bool(merge_runs))
+                                np.log2(encoder.per_level_scale), encoder.base_resolution, bool(contract), merge_runs)

@@ -97,6 +97,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step (config 5: 65,536 / 8)")
+    ap.add_argument("--merge-runs", default="off", choices=["off", "interval", "ray"], help="pooled-encode backward variant")
     a = ap.parse_args()
     import torch.distributed as dist
     from ucnerf_b200 import _lib
@@ -125,7 +126,8 @@ def main():
         if timed:
             ph.mark("start")
         opt.zero_grad(set_to_none=True)
-        renderings, ray_history = level_loop(model, True, batch, 0.5, compute_extras=False, hash_decay=False, generator=gen)
+        renderings, ray_history = level_loop(model, True, batch, 0.5, compute_extras=False, hash_decay=False, generator=gen,
+                                              merge_runs={"off": False, "interval": True, "ray": "ray"}[a.merge_runs])
         loss = compute_loss(batch, renderings, ray_history)
         if timed:
             ph.mark("forward")
@@ -178,7 +180,7 @@ def main():
             "bench": "train_step (BASELINE.json configs[4])", "metric": "train_rays_per_sec",
             "value": world * n * a.steps / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "rays_per_gpu_per_step": n, "samples_per_ray": wl.samples_per_ray,
-            "scaling": "weak", "dtype": "f32", "data": "synthetic", "phase_ms_per_step": phases,
+            "scaling": "weak", "dtype": "f32", "pooled_backward": a.merge_runs, "data": "synthetic", "phase_ms_per_step": phases,
             "native_launches_per_step": (_lib.launch_count() - launches0) / a.steps, "final_loss": float(loss.detach()),
             "note": "forward / backward through ucnerf_b200.train_forward.level_loop (native resample, cast_rays, pooled "
                     "encode, composite; nn.Linear layers in cuBLAS fp32), torch Adam for the dense layers, fused "

@@ -11,6 +11,7 @@ timeout 150 python -m pytest tests/test_train_pooled_encode.py tests/test_train_
 echo "rc=$?" >> gpurun_out/n1_train_pytest.log
 timeout 60 python bench_pooled.py --reps 5 > gpurun_out/n1_bench_pooled.log 2>&1
 timeout 90 python bench_train.py --steps 10 --warmup 3 > gpurun_out/n1_bench_train.log 2>&1
+timeout 60 python bench_train.py --steps 10 --warmup 3 --merge-runs ray > gpurun_out/n1_bench_train_rayruns.log 2>&1
 # per-launch times of one training step (shares of the step; serialised, cold caches)
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/n1_train_launches.csv \
     python bench_train.py --steps 1 --warmup 1 > gpurun_out/n1_ncu_train.log 2>&1

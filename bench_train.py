@@ -102,6 +102,7 @@ def main():
     import torch.distributed as dist
     from ucnerf_b200 import _lib
     from ucnerf_b200.gridencoder.optim import GridAdam
+    from ucnerf_b200.parallel_train import allreduce_gradients
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     if not torch.cuda.is_available():
         sys.exit("bench_train.py needs a CUDA device: the training ops have no CPU path")
@@ -135,16 +136,7 @@ def main():
         if timed:
             ph.mark("backward")
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in dense])
-            dist.all_reduce(flat)
-            flat /= world
-            off = 0
-            for p in dense:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
-            for e in encoders:
-                dist.all_reduce(e.embeddings.grad)
-                e.embeddings.grad /= world
+            allreduce_gradients(dense, [e.embeddings for e in encoders])
             if timed:
                 ph.mark("exchange")
         opt.step()

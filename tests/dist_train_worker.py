@@ -1,0 +1,46 @@
+"""Worker for the world_size-2 gloo test of the training step's gradient exchange (ucnerf_b200.parallel_train)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from ucnerf_b200.parallel_train import allreduce_gradients  # noqa: E402
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    g = torch.Generator().manual_seed(0)
+    shapes = [(64, 24), (64,), (1, 64), (3, 256), (0,)]
+    dense = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+    tables = [torch.nn.Parameter(torch.zeros((1000, 4))), torch.nn.Parameter(torch.zeros((32, 4)))]
+    base_d = [torch.randn(s, generator=g) for s in shapes]
+    base_t = [torch.randn(p.shape, generator=g) for p in tables]
+    for p, b in zip(dense, base_d):
+        p.grad = b * (rank + 1)                          # rank r holds (r + 1) * base -> mean = (world + 1) / 2 * base
+    for p, b in zip(tables, base_t):
+        p.grad = (b * (rank + 1)).t().contiguous().t()   # a non-contiguous gradient must come back in place too
+    dense[1].grad = None                                 # a parameter without a gradient is skipped
+    sent = allreduce_gradients(dense, tables)
+    k = (world + 1) / 2
+    for i, (p, b) in enumerate(zip(dense, base_d)):
+        if i == 1:
+            assert p.grad is None
+        else:
+            assert torch.allclose(p.grad, b * k, atol=1e-6), i
+    for p, b in zip(tables, base_t):
+        assert torch.allclose(p.grad, b * k, atol=1e-6)
+    expect = 4 * (sum(b.numel() for i, b in enumerate(base_d) if i != 1) + sum(b.numel() for b in base_t))
+    assert sent == expect, (sent, expect)
+    dist.barrier()
+    if rank == 0:
+        print(f"TRAIN_EXCHANGE_OK gloo {world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,7 @@
 """Host-side mirror of the reference's model classes (internal/models.py: `Model` L28-95, `MLP` L367-483, `NerfMLP`,
 `PropMLP`) for the configuration this package supports: the same class attributes (set as keyword arguments, the way gin
-sets them), the same sub-module and parameter names - a reference checkpoint loads with `load_state_dict` - and the same
+sets them), the same sub-module and parameter names - a reference checkpoint loads with `load_state_dict`
+(`strict=False` when it also carries the heads' `skynerf.*` / `brightness_corr.*` entries) - and the same
 `forward(rand, batch, train_frac, compute_extras, zero_glo=True, eval_camidx=None) -> (renderings, ray_history)`.
 The compute is not here: training mode runs `train_forward.level_loop` (native resampling, cast_rays, pooled hash-grid
 encode, compositing around this module's `nn.Linear` layers), eval mode the fused render path (`render.HotPathModel`).

@@ -97,7 +97,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step (config 5: 65,536 / 8)")
-    ap.add_argument("--merge-runs", default="off", choices=["off", "interval", "ray"], help="pooled-encode backward variant")
+    ap.add_argument("--merge-runs", default="auto", choices=["auto", "off", "interval", "ray"], help="pooled-encode backward variant")
     a = ap.parse_args()
     import torch.distributed as dist
     from ucnerf_b200 import _lib
@@ -128,7 +128,7 @@ def main():
             ph.mark("start")
         opt.zero_grad(set_to_none=True)
         renderings, ray_history = level_loop(model, True, batch, 0.5, compute_extras=False, hash_decay=False, generator=gen,
-                                              merge_runs={"off": False, "interval": True, "ray": "ray"}[a.merge_runs])
+                                              merge_runs={"auto": "auto", "off": False, "interval": True, "ray": "ray"}[a.merge_runs])
         loss = compute_loss(batch, renderings, ray_history)
         if timed:
             ph.mark("forward")

@@ -1,7 +1,9 @@
 """TEST INFRASTRUCTURE - import the *unmodified* reference Python hot path on CPU.
 
-Only usable where /root/reference exists (the build container); used by oracle/make_golden.py to
-pin oracle/ucnerf_oracle.py and to generate tests/golden/*.npz.  Nothing on the GPU box imports it.
+Resolves the reference tree from /root/reference (build container) or from the byte-identical staged copy
+baseline/_ref/nerf (baseline/stage_ref.py; git-ignored, shipped to the GPU box).  Used by oracle/make_golden.py to
+pin oracle/ucnerf_oracle.py and to generate tests/golden/*.npz, by tests/test_gpu_reference_modules.py (the reference's
+own modules on the drop-in kernels) and by bench.py's reference legs.  The product package never imports it.
 
 The reference needs 12 third-party modules that are absent here and a native `_gridencoder`
 backend that has no CPU implementation (gridencoder.cu:L15,L449-452).  We install inert stubs
@@ -19,7 +21,11 @@ import types
 import numpy as np
 import torch
 
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_ROOT = "/root/reference/nerf"
+if not os.path.isdir(os.path.join(REF_ROOT, "internal")):
+    REF_ROOT = os.path.join(_REPO, "baseline", "_ref", "nerf")
+REF_CUDA_SO = os.path.join(_REPO, "oracle", "_ref", "_gridencoder_ref.so")
 
 
 def available():
@@ -135,22 +141,64 @@ def _install_grid_backend():
                                      weight, B, D, C, L, S, H, gridtype, align_corners)
         grad.copy_(torch.from_numpy(out))
 
-    _stub("_gridencoder", grid_encode_forward=grid_encode_forward, grid_encode_backward=grid_encode_backward,
-          grad_total_variation=grad_total_variation)
+    return _stub("_gridencoder", grid_encode_forward=grid_encode_forward, grid_encode_backward=grid_encode_backward,
+                 grad_total_variation=grad_total_variation)
+
+
+_BACKENDS = {}
+
+
+def grid_backend(kind):
+    """The module the reference's grid.py binds as `_backend` (gridencoder/grid.py:L9-12):
+      "oracle"   - CPU stand-in (the oracle's restatement of kernel_grid; the reference has no CPU kernel),
+      "ref_cuda" - the reference's own gridencoder.cu compiled for sm_100a (oracle/build_ref.py),
+      "dropin"   - ucnerf_b200/dropin/_gridencoder.py, i.e. the product kernels behind the reference's module name."""
+    if kind in _BACKENDS:
+        return _BACKENDS[kind]
+    if kind == "oracle":
+        prev = sys.modules.get("_gridencoder")
+        m = _install_grid_backend()
+        if prev is not None:
+            sys.modules["_gridencoder"] = prev
+    elif kind == "ref_cuda":
+        import importlib.util
+        if not os.path.exists(REF_CUDA_SO):
+            raise RuntimeError("oracle/_ref/_gridencoder_ref.so not built (oracle/build_ref.py)")
+        spec = importlib.util.spec_from_file_location("_gridencoder_ref", REF_CUDA_SO)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    elif kind == "dropin":
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            "_gridencoder_dropin", os.path.join(_REPO, "ucnerf_b200", "dropin", "_gridencoder.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    else:
+        raise KeyError(kind)
+    _BACKENDS[kind] = m
+    return m
+
+
+def use_grid_backend(kind):
+    """Re-bind the (already imported, unmodified) reference grid.py to another native backend."""
+    R = load_reference()
+    R.grid._backend = grid_backend(kind)
+    return R
 
 
 _MODELS = None
 
 
-def load_reference():
-    """Returns the reference modules (models, configs, render, stepfun, coord, math, grid)."""
+def load_reference(backend="oracle"):
+    """Returns the reference modules (models, configs, render, stepfun, coord, math, grid); `backend` = what the
+    reference's `import _gridencoder` resolves to at first import (see grid_backend / use_grid_backend)."""
     global _MODELS
     if _MODELS is not None:
         return _MODELS
     if not available():
         raise RuntimeError("reference tree not present")
     _install_stubs()
-    _install_grid_backend()
+    sys.modules["_gridencoder"] = grid_backend(backend)
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     import warnings
@@ -209,6 +257,29 @@ def inject_rand_vec(rand_vec):
     def patched(t, *a, **k):
         if tuple(t.shape) == tuple(rand_vec.shape):
             return rand_vec.clone()
+        return orig(t, *a, **k)
+
+    torch.randn_like = patched
+    try:
+        yield
+    finally:
+        torch.randn_like = orig
+
+
+@contextlib.contextmanager
+def inject_rand_vec_rows(cam_dirs_full, rand_vec_full):
+    """Same for a chunked render (`render_image` slices the flat batch into views, models.py:L939-953): a call
+    `randn_like(chunk_of_cam_dirs)` gets the rows of `rand_vec_full` that the chunk occupies in `cam_dirs_full`."""
+    orig = torch.randn_like
+    base, nbytes = cam_dirs_full.data_ptr(), cam_dirs_full.numel() * cam_dirs_full.element_size()
+    row = cam_dirs_full.shape[-1] * cam_dirs_full.element_size()
+    flat = rand_vec_full.reshape(-1, rand_vec_full.shape[-1])
+
+    def patched(t, *a, **k):
+        off = t.data_ptr() - base
+        if t.dim() == 2 and t.shape[-1] == flat.shape[-1] and 0 <= off < nbytes and off % row == 0 and t.is_contiguous():
+            r0 = off // row
+            return flat[r0:r0 + t.shape[0]].to(t.device).clone()
         return orig(t, *a, **k)
 
     torch.randn_like = patched

@@ -111,7 +111,7 @@ def main():
 
             def render_rays(self, batch, train_frac, rand_vec, want):
                 out = super().render_rays(batch, train_frac, rand_vec, want)
-                if FakeAffine.affine is not None:
+                if FakeAffine.affine is not None and "packed" in out:
                     a = FakeAffine.affine
                     out["packed"][:, 0:3] = out["packed"][:, 0:3] @ a[:3, :3].T + a[:3, 3]
                 return out
@@ -127,7 +127,7 @@ def main():
                                rand_vec=torch.zeros(H * W, 3))
         for k in ("rgb", "sky_rgbs", "acc", "depth"):
             assert torch.allclose(img_h[k], ref_h[k], atol=1e-6), k
-        assert img_h["sky_rgbs"].shape == (H, W, 3) and img_h["affine_trans_sky"].shape == (H * W, 3, 4)
+        assert img_h["sky_rgbs"].shape == (H, W, 3) and img_h["affine_trans_sky"].shape == (H, W, 3, 4)
         assert not torch.allclose(img_h["rgb"], img["rgb"])
     else:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))

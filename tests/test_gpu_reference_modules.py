@@ -1,0 +1,195 @@
+"""GPU: the reference's OWN, unmodified Python (gridencoder/grid.py, internal/models.py `Model` / `render_image`)
+running on the drop-in, against the same modules running on the reference's own CUDA kernel.
+
+The reference tree is resolved by oracle/ref_shim.py from /root/reference or from the byte-identical staged copy
+baseline/_ref/nerf (baseline/stage_ref.py; git-ignored, shipped to the GPU box by gpurun).  Three backends can sit
+behind the reference's `import _gridencoder` (gridencoder/grid.py:L9-12):
+  "dropin"   - ucnerf_b200/dropin/_gridencoder.py  (the product kernels)
+  "ref_cuda" - oracle/_ref/_gridencoder_ref.so      (gridencoder.cu compiled for sm_100a, the checker)
+What is asserted:
+  1. grid.py:L24-89,L158-174 (`_grid_encode` forward + backward, `GridEncoder.forward`, `grad_total_variation`) give the
+     same numbers on both backends;
+  2. the reference `Model.forward` (models.py:L97-365) on the drop-in kernels == on the reference kernel;
+  3. `ucnerf_b200.render.render_image(<reference Model>, ...)` == the reference's `models.render_image`
+     (models.py:L907-1007) on the same weights and injected rand_vec: rgb / acc / pre-threshold depth L-inf < 1e-4,
+     every key and shape of the returned dict, heads off and on;
+  4. the cached renderer follows the live parameters (train.py:L330 renders between optimiser steps)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import cases, ref_shim, ucnerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+needs_ref = pytest.mark.skipif(not ref_shim.available() or not os.path.exists(ref_shim.REF_CUDA_SO),
+                               reason="reference tree / reference kernel not staged (baseline/stage_ref.py, oracle/build_ref.py)")
+
+
+def test_staged_reference_is_byte_identical_to_the_manifest():
+    """What runs here is the reference as it lies under /root/reference (sha256 recorded at staging time)."""
+    man = os.path.join(ROOT, "baseline", "_ref", "MANIFEST.json")
+    if not os.path.exists(man):
+        pytest.skip("baseline/_ref not staged")
+    m = json.load(open(man))
+    assert len(m) >= 20
+    for rel, sha in m.items():
+        data = open(os.path.join(ROOT, "baseline", "_ref", "nerf", rel), "rb").read()
+        assert hashlib.sha256(data).hexdigest() == sha, rel
+
+
+@needs_ref
+def test_reference_grid_py_runs_on_the_dropin_backend():
+    """grid.py:L158-174 / L24-89 executed by the reference's own classes with `_backend` = the drop-in."""
+    out = {}
+    for kind in ("dropin", "ref_cuda"):
+        R = ref_shim.use_grid_backend(kind)
+        assert R.grid._backend is ref_shim.grid_backend(kind)
+        torch.manual_seed(0)
+        enc = R.grid.GridEncoder(input_dim=3, num_levels=6, level_dim=4, per_level_scale=2, base_resolution=16,
+                                 log2_hashmap_size=19, desired_resolution=512, gridtype='hash', align_corners=False,
+                                 interpolation='linear', init_std=0.5).cuda()
+        g = torch.Generator().manual_seed(1)
+        x = (torch.rand((5000, 3), generator=g) * 2 - 1).cuda().requires_grad_(True)
+        y = enc(x, bound=1)                                     # GridEncoder.forward -> _grid_encode.apply
+        (y.square().sum() + y.sum()).backward()
+        ge = enc.embeddings.grad.clone()
+        enc.embeddings.grad.zero_()
+        out[kind] = (y.detach().cpu(), ge.cpu(), x.grad.detach().cpu(), type(enc).__module__)
+    assert out["dropin"][3] == "gridencoder.grid"               # the reference's class, not our mirror
+    assert torch.equal(out["dropin"][0], out["ref_cuda"][0])    # forward: bit-identical
+    scale = float(out["ref_cuda"][1].abs().max())
+    assert float((out["dropin"][1] - out["ref_cuda"][1]).abs().max()) < 2e-5 * max(scale, 1.0)   # atomics reorder
+    assert float((out["dropin"][2] - out["ref_cuda"][2]).abs().max()) < 2e-4 * max(1.0, float(out["ref_cuda"][2].abs().max()))
+
+
+def _reference_model(name, n_rays, heads=False, device="cuda"):
+    cfg, params, batch = cases.make_case(name, n_rays)
+    model, conf = ref_shim.build_reference_model(cfg, params)
+    R = ref_shim.load_reference()
+    if heads:
+        conf = R.configs.Config()
+        conf.brightness_correction, conf.model_sky, conf.training_views = True, True, 9
+        model = R.models.Model(config=conf)
+        hw = cases.make_heads(seed=3, n_views=9)
+        sd = model.state_dict()
+        model.load_state_dict({k: (params.get(k, hw.get(k)) if not k.endswith('.idx') else v).to(v.dtype)
+                               for k, v in sd.items()})
+        model.eval()
+    conf.render_chunk_size = 1000       # several chunks, the last one ragged
+    conf.vis_num_rays = 8
+    return cfg, model.to(device), conf, batch
+
+
+@needs_ref
+def test_reference_model_forward_on_dropin_equals_reference_kernel():
+    cfg, model, conf, batch = _reference_model("waymo", 300)
+    b = {k: v.cuda() for k, v in batch.items() if k != "rand_vec"}
+    rv = batch["rand_vec"].cuda()
+    res = {}
+    for kind in ("ref_cuda", "dropin"):
+        ref_shim.use_grid_backend(kind)
+        with torch.no_grad(), ref_shim.inject_rand_vec(rv):
+            rr, rh = model(False, b, train_frac=1.0, compute_extras=True, zero_glo=True)
+        res[kind] = (rr, rh)
+    for k in ("rgb", "acc", "depth", "distance_mean", "distance_median"):
+        assert torch.equal(res["dropin"][0][-1][k], res["ref_cuda"][0][-1][k]), k
+    for l in range(2):
+        assert torch.equal(res["dropin"][1][l]["sdist"], res["ref_cuda"][1][l]["sdist"])
+        assert torch.equal(res["dropin"][1][l]["weights"], res["ref_cuda"][1][l]["weights"])
+    # and the reference on the GPU agrees with the oracle restatement that the goldens pin on the CPU
+    orr, _ = O.model_forward(cases.make_case("waymo", 300)[1], cfg, batch)
+    assert float((res["ref_cuda"][0][-1]["rgb"].cpu() - orr[-1]["rgb"]).abs().max()) < 1e-4
+
+
+class _Acc:
+    process_index, num_processes, is_main_process = 0, 1, True
+
+    def autocast(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def gather(self, v):
+        return v
+
+
+@needs_ref
+@pytest.mark.parametrize("heads", [False, True], ids=["plain", "sky+brightness"])
+def test_render_image_dropin_matches_reference_render_image(heads):
+    """Seam 2: same call, same dict.  H x W = 37 x 61 = 2,257 rays -> 3 reference chunks of 1000 (last ragged)."""
+    from ucnerf_b200 import render as R2
+    H, W = 37, 61
+    cfg, model, conf, batch = _reference_model("waymo", H * W, heads=heads)
+    R = ref_shim.use_grid_backend("ref_cuda")
+    b2d = {k: v.reshape(H, W, -1).cuda() for k, v in batch.items() if k != "rand_vec"}
+    rv = batch["rand_vec"].cuda()
+    cam = torch.tensor(4, device="cuda")
+    flat_cam_dirs = b2d["cam_dirs"].reshape(H * W, 3)
+    torch.manual_seed(7)
+    with ref_shim.inject_rand_vec_rows(flat_cam_dirs, rv):
+        ref = R.models.render_image(model, _Acc(), dict(b2d), False, 1.0, conf, verbose=False, return_weights=True,
+                                    eval_camidx=cam)
+    torch.manual_seed(7)
+    img = R2.render_image(model, _Acc(), dict(b2d), False, 1.0, conf, verbose=False, return_weights=True,
+                          eval_camidx=cam, rand_vec=rv)
+    assert set(img.keys()) == set(ref.keys()), (sorted(img.keys()), sorted(ref.keys()))
+    for k, v in ref.items():
+        if k.startswith("ray_"):
+            assert len(img[k]) == len(v)
+            for a, bb in zip(img[k], v):
+                assert tuple(a.shape) == tuple(bb.shape), (k, a.shape, bb.shape)
+        else:
+            assert tuple(img[k].shape) == tuple(v.shape), (k, img[k].shape, v.shape)
+    tol = {"rgb": 1e-4, "acc": 1e-4, "weights": 1e-4, "coord": 1e-4, "sky_rgbs": 2e-4, "affine_trans": 1e-6,
+           "affine_trans_sky": 1e-6, "distance_mean": 5e-4, "distance_median": 5e-4, "distance_percentile_5": 5e-4,
+           "distance_percentile_95": 5e-4}
+    for k, t in tol.items():
+        if k in ref:
+            err = float((img[k] - ref[k]).abs().max())
+            assert err < t, (k, err)
+    # depth: the reference overrides depth where acc < 0.6 (render.py:L208,L213); compare away from the threshold
+    clear = (ref["acc"] - 0.6).abs() > 1e-3
+    assert float((img["depth"] - ref["depth"])[clear].abs().max()) < 1e-4 * max(1.0, float(ref["depth"][clear & (ref["depth"] < 299)].abs().max() if (clear & (ref["depth"] < 299)).any() else 1.0))
+    # same random bundle of rays (both sides draw `torch.randperm(num_rays)[:vis_num_rays]` from the seeded generator)
+    for l in range(2):
+        assert float((img["ray_sdist"][l] - ref["ray_sdist"][l]).abs().max()) < 1e-4
+        assert float((img["ray_weights"][l] - ref["ray_weights"][l]).abs().max()) < 1e-4
+        assert float((img["ray_rgbs"][l] - ref["ray_rgbs"][l]).abs().max()) < 1e-4
+
+
+@needs_ref
+def test_cached_renderer_follows_the_live_parameters():
+    """train.py:L330 calls render_image between optimiser steps: the handle cached on the module must be refreshed when
+    a dense weight changes in place (optimiser step) and after load_state_dict."""
+    from ucnerf_b200 import render as R2
+    H, W = 8, 16
+    cfg, model, conf, batch = _reference_model("waymo", H * W)
+    R = ref_shim.use_grid_backend("ref_cuda")
+    b2d = {k: v.reshape(H, W, -1).cuda() for k, v in batch.items() if k != "rand_vec"}
+    rv = batch["rand_vec"].cuda()
+    flat_cam_dirs = b2d["cam_dirs"].reshape(H * W, 3)
+
+    def both():
+        with ref_shim.inject_rand_vec_rows(flat_cam_dirs, rv):
+            ref = R.models.render_image(model, _Acc(), dict(b2d), False, 1.0, conf, verbose=False)
+        img = R2.render_image(model, _Acc(), dict(b2d), False, 1.0, conf, verbose=False, rand_vec=rv)
+        return float((img["rgb"] - ref["rgb"]).abs().max()), img["rgb"].clone()
+
+    e0, rgb0 = both()
+    assert e0 < 1e-4
+    with torch.no_grad():                                   # an "optimiser step" on dense layers only
+        model.nerf_mlp.rgb_layer.weight.mul_(0.5)
+        model.nerf_mlp.density_layer[2].bias.add_(0.3)
+        model.prop_mlp_0.density_layer[0].weight.mul_(1.1)
+    e1, rgb1 = both()
+    assert float((rgb1 - rgb0).abs().max()) > 1e-3          # the change is visible ...
+    assert e1 < 1e-4                                        # ... and identical to the reference's
+    sd = {k: (v * 0.9 if k.endswith("lin_second_stage_0.weight") else v) for k, v in model.state_dict().items()}
+    model.load_state_dict(sd)
+    e2, _ = both()
+    assert e2 < 1e-4

@@ -86,13 +86,14 @@ class _pooled_encode(Function):
         return None, None, grad_emb, None, None, None, None, None, None
 
 
-def pooled_encode(encoder, means, stds, contract=True, merge_runs=False):
+def pooled_encode(encoder, means, stds, contract=True, merge_runs=True):
     """`encoder`: a GridEncoder (this package's mirror or the reference's own class - only `embeddings`, `offsets`,
     `grid_sizes`, `per_level_scale`, `base_resolution` and the configuration attributes are read).
     `merge_runs`: backward variants that combine the contributions of consecutive points sharing a cell before the atomic
     reductions - True: within an interval, 'ray': across 4 consecutive intervals (rows must be ordered ray by ray, sample
-    by sample, as render.cast_rays produces them) - same gradient up to fp32 summation order; not yet measured on a GPU,
-    hence off by default.
+    by sample, as render.cast_rays produces them) - same gradient up to fp32 summation order.  Measured on B200
+    (profiles/r2_pooled_encode.json, forward + backward): proposal level 9.67 ms plain / 2.39 ms True / 2.20 ms 'ray';
+    NeRF level 2.67 / 1.08 / 1.13 ms - hence on by default; False keeps the one-reduction-per-point form.
     Returns (features [..., L*C], coord [..., 3])."""
     _check(encoder.input_dim == 3 and encoder.level_dim == 4, "pooled_encode: input_dim 3 / level_dim 4 only")
     _check(getattr(encoder, "gridtype", "hash") == "hash" and not encoder.align_corners

@@ -442,12 +442,27 @@ def shard_bounds(num_rays: int, world: int, rank: int):
     return per, start, stop
 
 
+def _param_versions(module):
+    """Fingerprint of a module's parameters: in-place updates (optimiser steps, load_state_dict) bump `_version`,
+    re-assigned storage changes `data_ptr`."""
+    return tuple((p._version, p.data_ptr()) for p in module.parameters())
+
+
 def _get_renderer(model, config):
+    """The HotPathModel cached on the reference module.  ucnerf_model_create copies the MLP weights into library-owned
+    memory, so a cached handle goes stale when training continues between two test renders (train.py:L330 calls
+    render_image periodically) or after load_state_dict: the parameter versions are compared on every call and the
+    handle is refreshed when any moved."""
     m = model.module if hasattr(model, "module") else model
+    mods = [m.nerf_mlp] + [m.get_submodule(f'prop_mlp_{i}') for i in range(m.num_levels - 1)]
+    versions = tuple(_param_versions(x) for x in mods)
     r = getattr(m, "_ucnerf_b200_renderer", None)
     if r is None:
         r = HotPathModel.from_reference_model(m, config)
         object.__setattr__(m, "_ucnerf_b200_renderer", r)
+    elif versions != getattr(m, "_ucnerf_b200_renderer_versions", None):
+        r.refresh({k: v for k, v in m.state_dict().items()})
+    object.__setattr__(m, "_ucnerf_b200_renderer_versions", versions)
     return r
 
 
@@ -458,8 +473,8 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
     the affine is applied in the compositing kernel, with `config.model_sky` the reference's own sky head runs on top
     (keys `sky_rgbs`, `affine_trans`, `affine_trans_sky` as models.py:L336-363).
 
-    model: a reference `Model` (a HotPathModel is built from it once and cached on the module) or None when
-    `renderer` is given.  accelerator: only process_index / num_processes are read."""
+    model: a reference `Model` (a HotPathModel is built from it, cached on the module and refreshed whenever the
+    module's parameters changed since the previous call) or None when `renderer` is given.  accelerator: only process_index / num_processes are read."""
     if rand:
         raise NotImplementedError("render_image on the fused path is the deterministic eval path (rand=False)")
     r = renderer if renderer is not None else _get_renderer(model, config)
@@ -493,11 +508,28 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
         affine, affine_sky = (res[0][0], res[1][0]) if use_sky else (res[0], None)
         r.set_rgb_affine(affine)    # reset right after this image's render_rays
     nl = r.num_levels
-    want = ["packed"] + [f"sdist_{l}" for l in range(nl)] + [f"weights_{l}" for l in range(nl)] + ["sample_rgb"]
+    # Whole-image buffers: the packed pixels and - where the caller gets them or the sky blend reads them - the NeRF
+    # level's weights.  The per-sample bundles (`ray_sdist` / `ray_weights` / `ray_rgbs`) are wanted for vis_num_rays
+    # random rays only (models.py:L996-1005), so they come from a second render of just those rays below instead of
+    # materialising [rays, S+1] / [rays, S] / [rays, S, 3] for every level of every ray.
+    need_weights = world == 1 or return_weights or use_sky
+    want = ["packed"] + ([f"weights_{nl - 1}"] if need_weights else [])
     if return_weights:
         want.append("sample_coord")
+    nv = r.vis_num_rays
+    n_local = stop - start
+    # The reference keeps the first vis_num_rays rays of every render_chunk_size chunk (models.py:L286-295), concatenates
+    # them over the chunks and then draws `randperm(total)[:vis_num_rays]` (L996-1005): the same candidates and the same
+    # draw from torch's CPU generator here, so a seeded run shows the same bundle.  (With several ranks the reference's
+    # candidates are spread over its per-chunk rank slices; here they are this rank's tile - a random bundle either way.)
+    ref_chunk = int(getattr(config, "render_chunk_size", 16384) or 16384)
+    cand = (torch.arange(0, max(n_local, 1), ref_chunk)[:, None] + torch.arange(nv)[None, :])
+    cand = cand[(cand < max(n_local, 1)) & (torch.arange(nv)[None, :] < ref_chunk)]
+    pick = cand[torch.randperm(cand.numel())[:nv]].to(r.device)
+    vis_want = [f"sdist_{l}" for l in range(nl)] + [f"weights_{l}" for l in range(nl)] + ["sample_rgb"]
     try:
         out = r.render_rays(local, train_frac, lrv, want)
+        vis = r.render_rays({k: v[pick] for k, v in local.items()}, train_frac, lrv[pick], vis_want)
     finally:
         if affine is not None:
             r.set_rgb_affine(None)   # the affine belongs to this image only, also when the render raises
@@ -526,13 +558,13 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
         "distance_percentile_5": packed[:, 7].reshape(height, width),
         "distance_percentile_95": packed[:, 8].reshape(height, width),
     }
-    wl = out[f"weights_{nl - 1}"]
-    if world > 1 and return_weights:
-        import torch.distributed as dist
-        fw = torch.empty((world * per, wl.shape[1]), device=r.device, dtype=torch.float32)
-        dist.all_gather_into_tensor(fw, wl.contiguous())
-        wl = fw[:num_rays]
-    if world == 1 or return_weights:
+    if need_weights and (world == 1 or return_weights):
+        wl = out[f"weights_{nl - 1}"]
+        if world > 1:
+            import torch.distributed as dist
+            fw = torch.empty((world * per, wl.shape[1]), device=r.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(fw, wl.contiguous())
+            wl = fw[:num_rays]
         rendering["weights"] = wl.reshape(height, width, -1)
     if return_weights:   # models.py:L976-978: the NeRF level's sample coordinates for extract.py
         co = out["sample_coord"].reshape(out["sample_coord"].shape[0], -1)
@@ -543,20 +575,17 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
             co = fc[:num_rays]
         rendering["coord"] = co.reshape(height, width, -1, 3)
     # ray bundles for vis.visualize_suite: a random subset of vis_num_rays of this rank's rays per level
-    nv = r.vis_num_rays
-    n_local = stop - start
-    pick = torch.randperm(max(n_local, 1))[:nv].to(r.device)
-    final_rgb = torch.sum(out["sample_rgb"][pick] * out[f"weights_{nl - 1}"][pick][..., None], dim=-2)
-    rendering["ray_sdist"] = [out[f"sdist_{l}"][pick] for l in range(nl)]
-    rendering["ray_weights"] = [out[f"weights_{l}"][pick] for l in range(nl)]
+    final_rgb = torch.sum(vis["sample_rgb"] * vis[f"weights_{nl - 1}"][..., None], dim=-2)
+    rendering["ray_sdist"] = [vis[f"sdist_{l}"] for l in range(nl)]
+    rendering["ray_weights"] = [vis[f"weights_{l}"] for l in range(nl)]
     rendering["ray_rgbs"] = [final_rgb[:, None, :].expand(-1, r.samples[l], -1) for l in range(nl - 1)] + \
-                            [out["sample_rgb"][pick]]
+                            [vis["sample_rgb"]]
     if sky_rgbs is not None:
         rendering["sky_rgbs"] = sky_rgbs.reshape(height, width, 3)       # models.py:L336-337
     if affine is not None:
-        rendering["affine_trans"] = affine[None].expand(num_rays, 3, 4)   # models.py:L361-363
+        rendering["affine_trans"] = affine[None, None].expand(height, width, 3, 4)   # models.py:L361-363, L987-990
         if affine_sky is not None:
-            rendering["affine_trans_sky"] = affine_sky[None].expand(num_rays, 3, 4)
+            rendering["affine_trans_sky"] = affine_sky[None, None].expand(height, width, 3, 4)
     return rendering
 
 
@@ -566,12 +595,17 @@ def _sky_head(m, rays, config):
     reference's own torch head."""
     if not getattr(config, "ucnerf_reference_sky", False):
         head = getattr(m, "_ucnerf_b200_sky", None)
+        versions = _param_versions(m.skynerf)
+        if head and versions != getattr(m, "_ucnerf_b200_sky_versions", None):
+            head.close()         # sky weights moved (training step / load_state_dict): re-pack them
+            head = None
         if head is None:
             try:
                 head = SkyHead({"skynerf." + k: v for k, v in m.skynerf.state_dict().items()}, device=rays["origins"].device)
             except (NotImplementedError, KeyError):
                 head = False
             object.__setattr__(m, "_ucnerf_b200_sky", head)
+            object.__setattr__(m, "_ucnerf_b200_sky_versions", versions)
         if head:
             return head.render(rays["origins"], rays["directions"], rays["far"], rays["cam_dirs"])
     return _reference_sky_head(m, rays, getattr(config, "render_chunk_size", 16384))

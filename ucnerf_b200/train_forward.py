@@ -76,7 +76,7 @@ def _pos_enc(x, max_deg):
     return torch.cat([x, torch.sin(torch.cat([xb, xb + 0.5 * torch.pi], dim=-1))], dim=-1)
 
 
-def _mlp_forward(mlp, rand, means, stds, viewdirs, merge_runs=False):
+def _mlp_forward(mlp, rand, means, stds, viewdirs, merge_runs=True):
     """MLP.forward (models.py:L514-685) for the supported configuration; predict_density's front end is the fused op."""
     features, coord = pooled_encode(mlp.encoder, means, stds, merge_runs=merge_runs)   # L487-496, L512
     x = mlp.density_layer(features)                                               # L507
@@ -112,11 +112,12 @@ def _hash_decay(encoder):
 
 
 def level_loop(model, rand, batch, train_frac, compute_extras=False, hash_decay=True, generator=None, draws=None,
-               merge_runs=False):
+               merge_runs='auto'):
     """-> (renderings, ray_history), the lists Model.forward builds in its level loop.  `draws` (optional): one dict per
     level with the uniform / normal draws `jitter01`, `flip01`, `rot01`, `rand_vec` (testing / reproducibility); else
     they are drawn on the device with `generator`, in the reference's order.  `merge_runs`: backward variant of the
-    pooled encode (False / True / 'ray', see gridencoder.pooled.pooled_encode)."""
+    pooled encode (False / True / 'ray', see gridencoder.pooled.pooled_encode); 'auto' = the measured best per level:
+    'ray' on the proposal levels, True on the NeRF level."""
     _check_model(model, batch, compute_extras)
     lead = batch['origins'].shape[:-1]
     flat = lambda k, c: batch[k].reshape(-1, c)
@@ -155,7 +156,8 @@ def level_loop(model, rand, batch, train_frac, compute_extras=False, hash_decay=
         else:
             mlp = model.nerf_mlp
         _check_mlp(mlp)
-        ray_results = _mlp_forward(mlp, rand, means, stds, viewdirs, merge_runs)  # L222-229
+        mr = ('ray' if is_prop else True) if merge_runs == 'auto' else merge_runs
+        ray_results = _mlp_forward(mlp, rand, means, stds, viewdirs, mr)          # L222-229
         density, rgbs = ray_results['density'], ray_results['rgb']
         if scale_grads:                                                           # L232-234
             if rgbs is None:

@@ -91,27 +91,15 @@ class Phases:
         return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step (config 5: 65,536 / 8)")
-    ap.add_argument("--merge-runs", default="auto", choices=["auto", "off", "interval", "ray"], help="pooled-encode backward variant")
-    a = ap.parse_args()
+def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", native_mlp="auto"):
+    """One training step of config 5 timed on `dev` (process group already initialised when world > 1) -> result dict."""
     import torch.distributed as dist
     from ucnerf_b200 import _lib
     from ucnerf_b200.gridencoder.optim import GridAdam
     from ucnerf_b200.parallel_train import allreduce_gradients
-    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
-    if not torch.cuda.is_available():
-        sys.exit("bench_train.py needs a CUDA device: the training ops have no CPU path")
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    from ucnerf_b200.train_forward import level_loop
     model, wl = build_model(dev)
-    batch, n = make_batch(a.rays, seed=rank, dev=dev)
+    batch, n = make_batch(rays, seed=rank, dev=dev)
     encoders = [m.encoder for m in (model.prop_mlp_0, model.nerf_mlp)]
     table_ids = {id(e.embeddings) for e in encoders}
     dense = [p for p in model.parameters() if id(p) not in table_ids]
@@ -121,14 +109,15 @@ def main():
         e.embeddings.grad = torch.zeros_like(e.embeddings)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     ph = Phases()
+    mr = {"auto": "auto", "off": False, "interval": True, "ray": "ray"}[merge_runs]
+    kw = {} if native_mlp == "auto" else {"native_mlp": native_mlp == "on"}
 
     def step(timed):
-        from ucnerf_b200.train_forward import level_loop
         if timed:
             ph.mark("start")
         opt.zero_grad(set_to_none=True)
         renderings, ray_history = level_loop(model, True, batch, 0.5, compute_extras=False, hash_decay=False, generator=gen,
-                                              merge_runs={"auto": "auto", "off": False, "interval": True, "ray": "ray"}[a.merge_runs])
+                                              merge_runs=mr, **kw)
         loss = compute_loss(batch, renderings, ray_history)
         if timed:
             ph.mark("forward")
@@ -151,13 +140,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         step(False)
     sync_all()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         loss = step(True)
     e1.record()
     sync_all()
@@ -166,18 +155,42 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    phases = {k: v / steps for k, v in ph.totals().items()}
+    grad_bytes = sum(p.numel() for p in dense) * 4 + sum(e.embeddings.numel() for e in encoders) * 4
+    res = {"bench": "train_step (BASELINE.json configs[4])", "metric": "train_rays_per_sec",
+           "value": world * n * steps / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": steps,
+           "warmup": warmup, "ms_per_step": ms / steps, "rays_per_gpu_per_step": n, "samples_per_ray": wl.samples_per_ray,
+           "scaling": "weak", "dtype": "f32", "pooled_backward": merge_runs, "data": "synthetic", "phase_ms_per_step": phases,
+           "native_launches_per_step": (_lib.launch_count() - launches0) / steps, "final_loss": float(loss.detach()),
+           "gradient_allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
+           "note": "forward / backward through ucnerf_b200.train_forward.level_loop (native resample, cast_rays, pooled "
+                   "encode, composite and MLP kernels), torch Adam for the dense layers, fused hash-decay + Adam + zero_grad "
+                   "for the tables; N > 1 adds the gradient all-reduce DDP would do"}
+    del model, opt, grid_opt
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step (config 5: 65,536 / 8)")
+    ap.add_argument("--merge-runs", default="auto", choices=["auto", "off", "interval", "ray"], help="pooled-encode backward variant")
+    ap.add_argument("--native-mlp", default="auto", choices=["auto", "on", "off"], help="native MLP kernels vs nn.Linear (cuBLAS)")
+    a = ap.parse_args()
+    import torch.distributed as dist
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        sys.exit("bench_train.py needs a CUDA device: the training ops have no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    res = run(dev, world, rank, a.steps, a.warmup, a.rays, a.merge_runs, a.native_mlp)
     if rank == 0:
-        phases = {k: v / a.steps for k, v in ph.totals().items()}
-        print(json.dumps({
-            "bench": "train_step (BASELINE.json configs[4])", "metric": "train_rays_per_sec",
-            "value": world * n * a.steps / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms / a.steps, "rays_per_gpu_per_step": n, "samples_per_ray": wl.samples_per_ray,
-            "scaling": "weak", "dtype": "f32", "pooled_backward": a.merge_runs, "data": "synthetic", "phase_ms_per_step": phases,
-            "native_launches_per_step": (_lib.launch_count() - launches0) / a.steps, "final_loss": float(loss.detach()),
-            "note": "forward / backward through ucnerf_b200.train_forward.level_loop (native resample, cast_rays, pooled "
-                    "encode, composite; nn.Linear layers in cuBLAS fp32), torch Adam for the dense layers, fused "
-                    "hash-decay + Adam + zero_grad for the tables; N > 1 adds the gradient all-reduce DDP would do"}),
-              flush=True)
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -150,7 +150,9 @@ _BACKENDS = {}
 
 def grid_backend(kind):
     """The module the reference's grid.py binds as `_backend` (gridencoder/grid.py:L9-12):
-      "oracle"   - CPU stand-in (the oracle's restatement of kernel_grid; the reference has no CPU kernel),
+      "oracle"   - CPU stand-in (the oracle's numpy restatement of kernel_grid; the reference has no CPU kernel),
+      "oracle_c" - CPU stand-in for timing: forward through the C + OpenMP restatement oracle/grid_cpu.c (bit-identical
+                   to "oracle", tests/test_oracle_grid_c.py), backward / TV / dy_dx through the numpy one,
       "ref_cuda" - the reference's own gridencoder.cu compiled for sm_100a (oracle/build_ref.py),
       "dropin"   - ucnerf_b200/dropin/_gridencoder.py, i.e. the product kernels behind the reference's module name."""
     if kind in _BACKENDS:
@@ -160,6 +162,26 @@ def grid_backend(kind):
         m = _install_grid_backend()
         if prev is not None:
             sys.modules["_gridencoder"] = prev
+    elif kind == "oracle_c":
+        from oracle import build_c
+        base = grid_backend("oracle")
+
+        def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, dy_dx, gridtype,
+                                align_corners, interp):
+            if dy_dx is not None or embeddings.dtype != torch.float32:
+                return base.grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, dy_dx, gridtype,
+                                                align_corners, interp)
+            x, e, o = inputs.detach().contiguous(), embeddings.detach().contiguous(), offsets.to(torch.int32).contiguous()
+            assert outputs.is_contiguous() and outputs.dtype == torch.float32
+            rc = build_c.load().ucnerf_oracle_grid_forward_f32(x.data_ptr(), e.data_ptr(), o.data_ptr(), outputs.data_ptr(),
+                                                               B, D, C, L, float(S), int(H), int(gridtype),
+                                                               int(bool(align_corners)), int(interp))
+            if rc != 0:
+                raise RuntimeError("grid_cpu.c: unsupported input dimension")
+
+        m = _StubModule("_gridencoder_oracle_c")
+        m.__dict__.update(grid_encode_forward=grid_encode_forward, grid_encode_backward=base.grid_encode_backward,
+                          grad_total_variation=base.grad_total_variation)
     elif kind == "ref_cuda":
         import importlib.util
         if not os.path.exists(REF_CUDA_SO):

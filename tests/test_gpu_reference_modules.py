@@ -145,12 +145,14 @@ def test_render_image_dropin_matches_reference_render_image(heads):
                 assert tuple(a.shape) == tuple(bb.shape), (k, a.shape, bb.shape)
         else:
             assert tuple(img[k].shape) == tuple(v.shape), (k, img[k].shape, v.shape)
-    tol = {"rgb": 1e-4, "acc": 1e-4, "weights": 1e-4, "coord": 1e-4, "sky_rgbs": 2e-4, "affine_trans": 1e-6,
+    tol = {"rgb": 1e-4, "acc": 1e-4, "weights": 1e-4, "coord": 1e-4, "sky_rgbs": 1e-4, "affine_trans": 1e-6,
            "affine_trans_sky": 1e-6, "distance_mean": 5e-4, "distance_median": 5e-4, "distance_percentile_5": 5e-4,
            "distance_percentile_95": 5e-4}
     for k, t in tol.items():
         if k in ref:
             err = float((img[k] - ref[k]).abs().max())
+            if k == "sky_rgbs":   # the sky integral is unnormalised (decreasing depths, models.py:L872): relative, as tests/test_heads.py
+                err /= max(1.0, float(ref[k].abs().max()))
             assert err < t, (k, err)
     # depth: the reference overrides depth where acc < 0.6 (render.py:L208,L213); compare away from the threshold
     clear = (ref["acc"] - 0.6).abs() > 1e-3

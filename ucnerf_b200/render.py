@@ -442,6 +442,19 @@ def shard_bounds(num_rays: int, world: int, rank: int):
     return per, start, stop
 
 
+def gather_tiles(tile: torch.Tensor, world: int, num_rows: Optional[int] = None) -> torch.Tensor:
+    """The ONE collective of a multi-GPU render: every rank contributes its `[per, W]` tile,
+    every rank receives the `[world * per, W]` image (trimmed to `num_rows`, which drops the padding of the last tile).
+    `render_image` and `bench.py --gpus N` both call this."""
+    if world == 1:
+        return tile if num_rows is None else tile[:num_rows]
+    import torch.distributed as dist
+    tile = tile.contiguous()
+    full = torch.empty((world * tile.shape[0],) + tuple(tile.shape[1:]), device=tile.device, dtype=tile.dtype)
+    dist.all_gather_into_tensor(full, tile)
+    return full if num_rows is None else full[:num_rows]
+
+
 def _param_versions(module):
     """Fingerprint of a module's parameters: in-place updates (optimiser steps, load_state_dict) bump `_version`,
     re-assigned storage changes `data_ptr`."""
@@ -482,8 +495,9 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
     num_rays = height * width
     flat = {k: batch[k].reshape(num_rays, -1).to(r.device, non_blocking=True) for k in _RAY_KEYS}
     if rand_vec is None:
-        rv = batch.get('rand_vec')
-        rand_vec = rv.reshape(num_rays, 3).to(r.device) if rv is not None else None
+        rand_vec = batch.get('rand_vec')
+    if rand_vec is not None:
+        rand_vec = rand_vec.reshape(num_rays, 3).to(r.device, non_blocking=True)
     world = getattr(accelerator, "num_processes", 1) if accelerator is not None else 1
     rank = getattr(accelerator, "process_index", 0) if accelerator is not None else 0
     per, start, stop = shard_bounds(num_rays, world, rank)
@@ -541,14 +555,9 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
             sky_opacity = 1 - torch.sum(out[f"weights_{nl - 1}"], dim=-1, keepdim=True)
             packed[:, 0:3] += sky_opacity * (sky_rgbs @ affine_sky[:3, :3].T + affine_sky[:3, 3])
     if world > 1:
-        import torch.distributed as dist
-        full = torch.empty((world * per, PACKED_WIDTH), device=r.device, dtype=torch.float32)
-        dist.all_gather_into_tensor(full, packed)  # the ONE collective per image
-        packed = full[:num_rays]
+        packed = gather_tiles(packed, world, num_rays)      # the ONE collective per image
         if sky_rgbs is not None:
-            fs_ = torch.empty((world * per, 3), device=r.device, dtype=torch.float32)
-            dist.all_gather_into_tensor(fs_, sky_rgbs.contiguous())
-            sky_rgbs = fs_[:num_rays]
+            sky_rgbs = gather_tiles(sky_rgbs, world, num_rays)
     rendering = {
         "rgb": packed[:, 0:3].reshape(height, width, 3),
         "depth": packed[:, 3].reshape(height, width),
@@ -559,21 +568,10 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
         "distance_percentile_95": packed[:, 8].reshape(height, width),
     }
     if need_weights and (world == 1 or return_weights):
-        wl = out[f"weights_{nl - 1}"]
-        if world > 1:
-            import torch.distributed as dist
-            fw = torch.empty((world * per, wl.shape[1]), device=r.device, dtype=torch.float32)
-            dist.all_gather_into_tensor(fw, wl.contiguous())
-            wl = fw[:num_rays]
-        rendering["weights"] = wl.reshape(height, width, -1)
+        rendering["weights"] = gather_tiles(out[f"weights_{nl - 1}"], world, num_rays).reshape(height, width, -1)
     if return_weights:   # models.py:L976-978: the NeRF level's sample coordinates for extract.py
         co = out["sample_coord"].reshape(out["sample_coord"].shape[0], -1)
-        if world > 1:
-            import torch.distributed as dist
-            fc = torch.empty((world * per, co.shape[1]), device=r.device, dtype=torch.float32)
-            dist.all_gather_into_tensor(fc, co.contiguous())
-            co = fc[:num_rays]
-        rendering["coord"] = co.reshape(height, width, -1, 3)
+        rendering["coord"] = gather_tiles(co, world, num_rays).reshape(height, width, -1, 3)
     # ray bundles for vis.visualize_suite: a random subset of vis_num_rays of this rank's rays per level
     final_rgb = torch.sum(vis["sample_rgb"] * vis[f"weights_{nl - 1}"][..., None], dim=-2)
     rendering["ray_sdist"] = [vis[f"sdist_{l}"] for l in range(nl)]

@@ -116,7 +116,7 @@ def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", nati
         if timed:
             ph.mark("start")
         opt.zero_grad(set_to_none=True)
-        renderings, ray_history = level_loop(model, True, batch, 0.5, compute_extras=False, hash_decay=False, generator=gen,
+        renderings, ray_history = level_loop(model, True, batch, 0.5, compute_extras=False, hash_decay='fused', generator=gen,
                                               merge_runs=mr, **kw)
         loss = compute_loss(batch, renderings, ray_history)
         if timed:

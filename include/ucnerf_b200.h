@@ -78,6 +78,22 @@ int ucnerf_grid_adam_step(float* embeddings, float* grad, float* exp_avg, float*
                           const int32_t* offsets_host, uint32_t L, uint32_t C, double lr, double beta1, double beta2,
                           double eps, uint64_t step, double hash_decay_mult, int zero_grad, void* stream);
 
+/* Same with the reference's gradient clipping (train_utils.clip_gradients, L335-345) applied in the pass, before
+ * nan_to_num_(): g <- g * grad_scale (the global-norm coefficient min(1, max_norm / (norm + 1e-6)) of
+ * torch.nn.utils.clip_grad_norm_, computed by the caller over ALL parameters - this table's share of the squared norm
+ * comes from ucnerf_grid_table_stats), then clamp to +-grad_max_val (<= 0: off). */
+int ucnerf_grid_adam_step_clipped(float* embeddings, float* grad, float* exp_avg, float* exp_avg_sq,
+                                  const int32_t* offsets_host, uint32_t L, uint32_t C, double lr, double beta1,
+                                  double beta2, double eps, uint64_t step, double hash_decay_mult, int zero_grad,
+                                  double grad_scale, double grad_max_val, void* stream);
+
+/* One read pass over a table: out_sums[2 l] = sum over level l of p^2 and out_sums[2 l + 1] = sum of (g + c_l p)^2 with
+ * c_l = hash_decay_mult * 2 / (T_l L C) (grad may be NULL: zeros), device doubles [2 L].  From them:
+ *   loss_hash_decay (models.py:L297-306)           = sum_l out[2 l] / (T_l L C)
+ *   this table's squared gradient norm for clipping = sum_l out[2 l + 1]  (hash-decay gradient included). */
+int ucnerf_grid_table_stats(const float* embeddings, const float* grad, const int32_t* offsets_host, uint32_t L,
+                            uint32_t C, double hash_decay_mult, double* out_sums, void* stream);
+
 /* Pooled hash-grid encode for training (SURVEY.md section 8a rows R4 + R10): the front end of MLP.predict_density
  * (internal/models.py:L485-496) in one kernel each way.  means [B,M,3] / stds [B,M] are the multisample Gaussians
  * render.cast_rays returns (M = 6), device fp32; flags & UCNERF_POOLED_CONTRACT applies coord.contract_mean_std (coord.py:L60-72) and the

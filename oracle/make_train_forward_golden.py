@@ -3,7 +3,8 @@ in train() mode on CPU, with autograd (oracle/ref_shim.py: unmodified internal/m
 coord.py, gridencoder/grid.py; the native `_gridencoder` is the pinned CPU stand-in).  torch.rand / rand_like /
 randn_like are patched to return the stored draws (per level: jitter, flip mask, rotation, rand_vec - the reference's
 call order).  Stored: the draws, per-level sdist / weights / rgb / acc / loss_hash_decay, a scalar loss built from all
-of them, the gradients of the small layers in full and seeded projections of the large ones and of the embeddings.
+of them, the gradients of the small layers in full, seeded projections of the large ones and of the embeddings, and the
+embedding gradients ENTRY-WISE on a seeded sample of the table entries the rays touch (plus some they do not).
 
     python oracle/make_train_forward_golden.py        # writes tests/golden/train_forward.npz"""
 import os
@@ -16,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import cases, ref_shim  # noqa: E402
 
-N_RAYS, TRAIN_FRAC = 8, 0.3
+N_RAYS, TRAIN_FRAC = 256, 0.3
+N_ENTRIES = 8192   # table entries whose gradient is stored entry-wise (seeded sample of the entries the rays touch)
 FULL = ("density_layer.0.bias", "density_layer.2.bias", "rgb_layer.weight", "rgb_layer.bias", "density_layer.0.weight")
 
 
@@ -86,6 +88,21 @@ def main():
         if p.grad is None:
             continue
         short = name.split(".", 1)[1]
+        if name.endswith("embeddings"):
+            # entry-wise: entries whose gradient is more than the hash-decay term 0.1 * 2 p / (T_l L C) (i.e. touched by a
+            # ray) - a seeded sample of them - plus a few untouched ones
+            enc = model.get_submodule(name.rsplit(".", 1)[0])
+            T = (enc.offsets[1:] - enc.offsets[:-1]).double()
+            L = T.numel()
+            decay = 0.1 * 2.0 * p.detach().double() / (T[enc.idx.long()] * L * p.shape[1])[:, None]
+            touched = ((p.grad.double() - decay).abs().max(dim=1).values > 1e-12).nonzero()[:, 0]
+            gen = torch.Generator().manual_seed(len(name) + 1)
+            pick = touched[torch.randperm(touched.numel(), generator=gen)[:N_ENTRIES]]
+            extra = torch.randint(0, p.shape[0], (512,), generator=gen)
+            sel = torch.unique(torch.cat([pick, extra]))
+            out["gsel_idx_" + name] = sel.to(torch.int32).numpy()
+            out["gsel_val_" + name] = p.grad[sel].numpy()
+            out["gsel_touched_" + name] = np.int64(touched.numel())
         if name.endswith("embeddings") or short not in FULL:
             out["gproj_" + name] = projections(p.grad, seed=len(name))
         else:

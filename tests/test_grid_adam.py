@@ -69,3 +69,54 @@ def test_gpu_fused_step_matches_reference_recipe():
         assert torch.equal(torch.isfinite(v_got), fin)                       # the +inf gradient saturates both the same way
         rel = ((v_got[fin] - v_ref[fin]).abs() / (v_ref[fin].abs() + 1e-30)).max().item()
         assert rel < 1e-5, rel
+
+
+@pytest.mark.gpu
+def test_gpu_table_stats_and_clipped_step_match_torch_clipping():
+    """train_utils.clip_gradients (L335-345): clip_grad_norm_ over ALL parameters, clip_grad_value_, nan_to_num_, then Adam.
+    The fused path gets the tables' share of the norm from ucnerf_grid_table_stats (hash-decay gradient included) and
+    applies coefficient + value clamp inside the optimiser kernel."""
+    from ucnerf_b200.gridencoder.optim import GridAdam
+    emb, offsets, idx, g = _table(2)
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embeddings = torch.nn.Parameter(emb.clone().cuda())
+            self.register_buffer("offsets", offsets.clone())
+
+    enc = Enc()
+    dense = torch.nn.Parameter(torch.randn(37, 5, generator=g).cuda())
+    opt = GridAdam([enc], lr=0.01, betas=(0.9, 0.99), eps=1e-15, hash_decay_mult=0.1, zero_grad=True)
+    rg = torch.randn(emb.shape, generator=g) * 2e-2
+    dg = torch.randn(37, 5, generator=g) * 1e-2
+    max_norm, max_val = 0.5, 0.01
+    # reference recipe in torch
+    p_ref = emb.clone().requires_grad_(True)
+    d_ref = dense.detach().cpu().clone().requires_grad_(True)
+    loss_ref = O.hash_decay_loss(p_ref, idx)
+    (0.1 * loss_ref).backward()
+    p_ref.grad += rg
+    d_ref.grad = dg.clone()
+    sq_ref = float(p_ref.grad.double().square().sum())
+    torch.nn.utils.clip_grad_norm_([p_ref, d_ref], max_norm)
+    torch.nn.utils.clip_grad_value_([p_ref, d_ref], max_val)
+    ref_opt = torch.optim.Adam([p_ref], lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+    ref_opt.step()
+    # fused path
+    enc.embeddings.grad = rg.clone().cuda()
+    dense.grad = dg.clone().cuda()
+    st = opt.table_stats()[0]
+    assert abs(float(st["loss_hash_decay"]) - float(loss_ref)) < 1e-6 * max(1.0, abs(float(loss_ref)))
+    assert abs(float(st["grad_sq_norm"]) - sq_ref) < 1e-6 * sq_ref
+    coef = opt.clip_coefficient([dense], max_norm)
+    assert float(coef) < 1.0                                   # the clip is active in this case
+    assert torch.allclose(dense.grad.cpu(), d_ref.grad if max_val <= 0 else (dg * float(coef)), rtol=1e-5, atol=1e-9)
+    opt.step(grad_scale=coef, grad_max_val=max_val)
+    torch.cuda.synchronize()
+    err = (enc.embeddings.detach().cpu() - p_ref.detach()).abs().max().item()
+    assert err < 2e-6, err
+    # empty gradient: the loss value alone
+    enc.embeddings.grad = None
+    st2 = opt.table_stats()[0]
+    assert float(st2["grad_sq_norm"]) >= 0 and abs(float(st2["loss_hash_decay"]) - float(O.hash_decay_loss(enc.embeddings.detach().cpu(), idx))) < 1e-6

@@ -238,7 +238,7 @@ def test_cuda_equals_the_unfused_gridencoder_chain_and_errors(case):
     assert float((feats.detach() - chain.detach()).abs().max()) < 1e-4          # see the module docstring
     ref = enc.embeddings.grad
     assert float((g_fused - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
         pooled_encode(enc, means.cpu(), stds.cpu())
     with pytest.raises(RuntimeError):
         pooled_encode(enc, means[..., :2], stds)

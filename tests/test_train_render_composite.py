@@ -129,7 +129,7 @@ def test_cuda_op_partial_gradients_train_batch_and_errors():
     for a in (1800, 5000):                                       # empty + opaque rays / ordinary rays (see make_inputs)
         ref = oracle_autograd(*[None if x is None else x[a:a + 256] for x in inp])
         check((w[a:a + 256], rgb[a:a + 256], acc[a:a + 256], dd[a:a + 256], None), ref, False)
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
         composite(density, rgbs, t, dirs)                        # CPU tensors
     with pytest.raises(RuntimeError):
         composite(density.cuda(), rgbs.cuda(), t[:, :-1].cuda(), dirs.cuda())

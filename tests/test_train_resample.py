@@ -117,7 +117,7 @@ def test_cuda_op_training_batch_properties_and_errors():
     det = resample_level(t, w, S, 0.0064, True)
     ref = O.resample_level(t[:64].cpu(), w[:64].cpu(), S, 0.0064, True)
     assert float((det[:64].cpu() - ref).abs().max()) < 1e-5      # serial CPU instantiation on the same rays: 2.3e-6
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
         resample_level(t.cpu(), w.cpu(), S)
     with pytest.raises(RuntimeError):
         resample_level(t, w[:, :-1], S)

@@ -86,5 +86,5 @@ def test_cuda_op_train_batch_seeded_stream_and_errors(gold):
     assert bool((mean_t >= tc[:, :-1].double() - 1e-5).all()) and bool((mean_t <= tc[:, 1:].double() + 1e-5).all())
     axis = args[1][:, None, None, :] + t0[..., None] * args[2][:, None, None, :]
     assert float(((m0 - axis).norm(dim=-1) / (5e-4 * t0.clamp_min(1e-6))).max()) < 0.72      # radius * t / sqrt(2)
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
         cast_rays(t, o, d, cam, r, False)

@@ -99,7 +99,7 @@ EXPORTS = [
     "ucnerf_render_rays", "ucnerf_render_rays_host", "ucnerf_launch_count", "ucnerf_set_option",
     "ucnerf_get_timing", "ucnerf_generate_rays", "ucnerf_render_camera", "ucnerf_render_camera_host",
     "ucnerf_set_rgb_affine", "ucnerf_sky_create", "ucnerf_sky_destroy", "ucnerf_sky_render",
-    "ucnerf_grid_adam_step",
+    "ucnerf_grid_adam_step", "ucnerf_grid_adam_step_clipped", "ucnerf_grid_table_stats",
     "ucnerf_pooled_encode_forward",
     "ucnerf_pooled_encode_backward",
     "ucnerf_resample_intervals",
@@ -146,6 +146,9 @@ def load():
     lib.ucnerf_set_rgb_affine.argtypes = [vp, vp]
     lib.ucnerf_grid_adam_step.argtypes = [vp, vp, vp, vp, vp, u32, u32, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_uint64, C.c_double, C.c_int, vp]
+    lib.ucnerf_grid_adam_step_clipped.argtypes = [vp, vp, vp, vp, vp, u32, u32, C.c_double, C.c_double, C.c_double,
+                                                  C.c_double, C.c_uint64, C.c_double, C.c_int, C.c_double, C.c_double, vp]
+    lib.ucnerf_grid_table_stats.argtypes = [vp, vp, vp, u32, u32, C.c_double, vp, vp]
     lib.ucnerf_pooled_encode_forward.argtypes = [vp, vp, u32, u32, C.c_int, vp, vp, vp, u32, u32, C.c_float, u32, vp, vp, vp]
     lib.ucnerf_pooled_encode_backward.argtypes = [vp, vp, vp, u32, u32, C.c_int, vp, vp, u32, u32, C.c_float, u32, vp, vp]
     lib.ucnerf_resample_intervals.argtypes = [vp, vp, u32, i32, C.c_int, f32, f32, f32, i32, vp, vp, i32, vp, vp]

@@ -507,11 +507,7 @@ int launch_color_mlp_tc(const ColorTcParams& p_in, cudaStream_t st) {
     }
     ColorTcParams p = p_in;
     p.dbg = g_tc_dbg;
-    static bool configured = false;
-    if (!configured) {
-        UC_CUDA_OK(cudaFuncSetAttribute(color_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal));
-        configured = true;
-    }
+    UC_ENSURE_SMEM(kSmemTotal, color_mlp_tc_kernel);
     const uint32_t ntiles = (p.n_rows + kTileM - 1) / kTileM;
     const uint32_t blocks = ntiles < (uint32_t)kNumSMs ? ntiles : (uint32_t)kNumSMs;
     color_mlp_tc_kernel<<<blocks, kThreads, kSmemTotal, st>>>(p);

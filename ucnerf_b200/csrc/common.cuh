@@ -41,6 +41,24 @@ extern std::atomic<uint64_t> g_launch_count;
         }                                                                                         \
     } while (0)
 
+// Opt a kernel into > 48 KB of dynamic shared memory.  cudaFuncSetAttribute is per DEVICE (and context), so what has been
+// configured is remembered per device, not in one process-wide flag: a process that renders on several GPUs (or from
+// several threads; the call is idempotent) never launches an unconfigured kernel.  Usage: UC_ENSURE_SMEM(bytes, kernel<..>)
+#define UC_ENSURE_SMEM(bytes, ...)                                                                               \
+    do {                                                                                                         \
+        static std::atomic<size_t> _uc_cfg[64];                                                                  \
+        const size_t _uc_b = (size_t)(bytes);                                                                    \
+        if (_uc_b > 48 * 1024) {                                                                                 \
+            int _uc_dev = 0;                                                                                     \
+            UC_CUDA_OK(cudaGetDevice(&_uc_dev));                                                                 \
+            const int _uc_i = (_uc_dev >= 0 && _uc_dev < 64) ? _uc_dev : 63;                                     \
+            if (_uc_dev != _uc_i || _uc_cfg[_uc_i].load(std::memory_order_relaxed) < _uc_b) {                    \
+                UC_CUDA_OK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)_uc_b)); \
+                _uc_cfg[_uc_i].store(_uc_b, std::memory_order_relaxed);                                          \
+            }                                                                                                    \
+        }                                                                                                        \
+    } while (0)
+
 template <typename T>
 __host__ __device__ inline T div_up(T a, T b) {
     return (a + b - 1) / b;

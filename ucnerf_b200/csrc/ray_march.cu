@@ -34,11 +34,7 @@ int launch_resample(const ResampleParams& p, cudaStream_t st) {
     if (p.n_rays == 0) return 0;
     const size_t smem = kWarpsPerBlockRay * ResampleScratch::floats(p.n_prev, p.S) * sizeof(float);
     UC_REQUIRE(smem <= 227 * 1024, "resample: too many samples per ray for shared memory");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        UC_CUDA_OK(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    UC_ENSURE_SMEM(smem, resample_kernel);
     resample_kernel<<<div_up(p.n_rays, (uint32_t)kWarpsPerBlockRay), 32 * kWarpsPerBlockRay, smem, st>>>(p);
     UC_LAUNCH_CHECK();
     return 0;
@@ -249,12 +245,7 @@ color_mlp_simt_kernel(const __grid_constant__ ColorParams p) {
 
 template <int NP>
 static int launch_color_t(const ColorParams& p, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        UC_CUDA_OK(cudaFuncSetAttribute(color_mlp_simt_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)ColorSmem<NP>::bytes));
-        configured = true;
-    }
+    UC_ENSURE_SMEM(ColorSmem<NP>::bytes, color_mlp_simt_kernel<NP>);
     const uint32_t ntiles = div_up(p.n_rows, (uint32_t)kTileRows);
     const uint32_t blocks = ntiles < (uint32_t)kNumSMs ? ntiles : (uint32_t)kNumSMs;
     color_mlp_simt_kernel<NP><<<blocks, kColorThreads, ColorSmem<NP>::bytes, st>>>(p);
@@ -321,11 +312,7 @@ int launch_composite(const CompositeParams& p, cudaStream_t st) {
     if (p.n_rays == 0) return 0;
     const size_t smem = kWarpsPerBlockRay * CompositeScratch::floats(p.S) * sizeof(float);
     UC_REQUIRE(smem <= 227 * 1024, "composite: too many samples per ray for shared memory");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        UC_CUDA_OK(cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    UC_ENSURE_SMEM(smem, composite_kernel);
     composite_kernel<<<div_up(p.n_rays, (uint32_t)kWarpsPerBlockRay), 32 * kWarpsPerBlockRay, smem, st>>>(p);
     UC_LAUNCH_CHECK();
     return 0;

@@ -65,11 +65,7 @@ extern "C" int ucnerf_resample_intervals(const float* t_prev, const float* w_pre
     p.jitter_cols = jitter ? jitter_cols : 0; p.out_sdist = out_sdist;
     const size_t smem = kResampleOpWarps * ResampleScratch::floats(n_prev, S) * sizeof(float);
     UC_REQUIRE(smem <= 227 * 1024, "resample_intervals: too many bins / samples per ray for shared memory");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        UC_CUDA_OK(cudaFuncSetAttribute(resample_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    UC_ENSURE_SMEM(smem, resample_op_kernel);
     resample_op_kernel<<<div_up(n_rays, (uint32_t)kResampleOpWarps), 32 * kResampleOpWarps, smem, (cudaStream_t)stream>>>(p);
     UC_LAUNCH_CHECK();
     return 0;

@@ -414,14 +414,7 @@ static int launch_one_impl(const SampleParams& p, cudaStream_t st) {
     // measured on B200 (profiles/r1_summary.md): the re-mapped density layer pays on the proposal level only
     constexpr bool kRemap = UC_REMAP_PROP ? !NERF : false;
     constexpr size_t smem = sizeof(float) * ((64 + ((kRemap || RUNS) ? kSampleThreads : 0)) * (LMAX * 4 + 4) + 128);
-    if constexpr (smem > 48 * 1024) {
-        static bool configured = false;
-        if (!configured) {
-            UC_CUDA_OK(cudaFuncSetAttribute(sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap, RUNS>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
-    }
+    UC_ENSURE_SMEM(smem, sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap, RUNS>);
     sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap, RUNS><<<blocks, kSampleThreads, smem, st>>>(p);
     UC_LAUNCH_CHECK();
     return 0;

@@ -450,11 +450,7 @@ int launch_sky_mlp_tc(const SkyTcParams& p_in, cudaStream_t st) {
     SkyTcParams p = p_in;
     p.dbg = g_sky_dbg;
     if (const char* e = getenv("UCNERF_SKY_DEBUG")) p.debug_flags = (uint32_t)atoi(e);   // profiling experiments only
-    static bool configured = false;
-    if (!configured) {
-        UC_CUDA_OK(cudaFuncSetAttribute(sky_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal));
-        configured = true;
-    }
+    UC_ENSURE_SMEM(kSmemTotal, sky_mlp_tc_kernel);
     const uint32_t ntiles = (p.n_rows + kTileM - 1) / kTileM;
     const uint32_t blocks = ntiles < (uint32_t)kNumSMs ? ntiles : (uint32_t)kNumSMs;
     sky_mlp_tc_kernel<<<blocks, kThreads, kSmemTotal, st>>>(p);

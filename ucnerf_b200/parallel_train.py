@@ -9,15 +9,19 @@ import torch.distributed as dist
 
 def allreduce_gradients(dense_params, table_params=(), group=None):
     """Average the `.grad` of `dense_params` (one flat all-reduce) and of `table_params` (in place, one all-reduce
-    each) over the ranks of `group`.  Parameters without a gradient are skipped.  Returns the bytes this rank
-    contributed, for reporting."""
+    each) over the ranks of `group`.  A parameter without a gradient on this rank contributes zeros (what DDP does), so
+    every rank issues the same collectives with the same sizes whatever subset of its parameters received a gradient.
+    Returns the bytes this rank contributed, for reporting."""
     if not dist.is_available() or not dist.is_initialized():
         return 0
     world = dist.get_world_size(group)
     if world == 1:
         return 0
     sent = 0
-    dense = [p for p in dense_params if p.grad is not None]
+    dense = list(dense_params)
+    for p in dense:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
     if dense:
         flat = torch.cat([p.grad.reshape(-1) for p in dense])
         dist.all_reduce(flat, group=group)
@@ -30,7 +34,7 @@ def allreduce_gradients(dense_params, table_params=(), group=None):
         sent += flat.numel() * flat.element_size()
     for p in table_params:
         if p.grad is None:
-            continue
+            p.grad = torch.zeros_like(p)
         g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
         dist.all_reduce(g, group=group)
         g /= world

@@ -117,7 +117,9 @@ def level_loop(model, rand, batch, train_frac, compute_extras=False, hash_decay=
     level with the uniform / normal draws `jitter01`, `flip01`, `rot01`, `rand_vec` (testing / reproducibility); else
     they are drawn on the device with `generator`, in the reference's order.  `merge_runs`: backward variant of the
     pooled encode (False / True / 'ray', see gridencoder.pooled.pooled_encode); 'auto' = the measured best per level:
-    'ray' on the proposal levels, True on the NeRF level."""
+    'ray' on the proposal levels, True on the NeRF level.  `hash_decay`: True = the reference's differentiable term
+    (torch), 'fused' = its value from one native read pass without autograd (pair it with GridAdam(hash_decay_mult=...),
+    which applies the term's gradient inside the optimiser kernel), False = omit."""
     _check_model(model, batch, compute_extras)
     lead = batch['origins'].shape[:-1]
     flat = lambda k, c: batch[k].reshape(-1, c)
@@ -180,7 +182,11 @@ def level_loop(model, rand, batch, train_frac, compute_extras=False, hash_decay=
         for k in ('raw_grad_density', 'grad_pred', 'normals', 'normals_pred', 'roughness'):      # L676-685
             ray_results[k] = None
         if hash_decay and getattr(model, "training", False):                      # L297-306
-            ray_results['loss_hash_decay'] = _hash_decay(mlp.encoder)
+            if hash_decay == 'fused':   # value only (one native read pass); its gradient lives in GridAdam(hash_decay_mult)
+                from .gridencoder.optim import hash_decay_loss
+                ray_results['loss_hash_decay'] = hash_decay_loss(mlp.encoder)
+            else:
+                ray_results['loss_hash_decay'] = _hash_decay(mlp.encoder)
         renderings.append(rendering)
         ray_results['sdist'] = sdist.reshape(lead + (S + 1,)).clone()             # L309-311
         ray_results['weights'] = rendering['weights'].clone()

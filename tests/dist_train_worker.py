@@ -24,17 +24,18 @@ def main():
         p.grad = b * (rank + 1)                          # rank r holds (r + 1) * base -> mean = (world + 1) / 2 * base
     for p, b in zip(tables, base_t):
         p.grad = (b * (rank + 1)).t().contiguous().t()   # a non-contiguous gradient must come back in place too
-    dense[1].grad = None                                 # a parameter without a gradient is skipped
-    sent = allreduce_gradients(dense, tables)
+    if rank == 0:
+        dense[1].grad = None                             # missing on ONE rank only: it contributes zeros (what DDP does) and
+    sent = allreduce_gradients(dense, tables)            # every rank still issues identical collectives
     k = (world + 1) / 2
     for i, (p, b) in enumerate(zip(dense, base_d)):
         if i == 1:
-            assert p.grad is None
+            assert torch.allclose(p.grad, b * (k - 1.0 / world), atol=1e-6)   # rank 0's share (1 * base) is zero
         else:
             assert torch.allclose(p.grad, b * k, atol=1e-6), i
     for p, b in zip(tables, base_t):
         assert torch.allclose(p.grad, b * k, atol=1e-6)
-    expect = 4 * (sum(b.numel() for i, b in enumerate(base_d) if i != 1) + sum(b.numel() for b in base_t))
+    expect = 4 * (sum(b.numel() for b in base_d) + sum(b.numel() for b in base_t))
     assert sent == expect, (sent, expect)
     dist.barrier()
     if rank == 0:

@@ -145,10 +145,15 @@ def test_level_loop_matches_the_reference_training_forward_and_backward():
         got = p.grad.cpu()[sel]
         scale = float(ref.abs().max())
         err = float((got - ref).abs().max())
-        assert err <= 1e-2 * scale, (name, err, scale)      # same bar as the dense layers above (sdist round-off moves points)
         rel_l2 = float((got - ref).double().norm() / ref.double().norm())
         print(name, 'entry-wise: max err / max', err / scale, 'relative L2', rel_l2)
-        assert rel_l2 < 2e-3, (name, rel_l2)
+        # The first level's fenceposts are exact, so the proposal table sees atomic-order / run-merging round-off only.
+        # The NeRF level's fenceposts carry the resampler's round-off (< 4e-6 of s = 6 % of a finest-level cell at
+        # far = 8), which moves trilinear weights of single entries by percents while the field stays continuous:
+        # a loose per-entry bar, a tight one on the whole sampled vector.
+        bar_max, bar_l2 = (1e-4, 1e-5) if name.startswith("prop_mlp_0") else (5e-2, 5e-3)
+        assert err <= bar_max * scale, (name, err, scale)
+        assert rel_l2 < bar_l2, (name, rel_l2)
         assert int(g["gsel_touched_" + name]) > 10000
 
 

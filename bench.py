@@ -306,7 +306,12 @@ def rooflines(wl, n, steps, fam, chunk_rays_opt):
                       "algorithmic_flops_per_launch": total / launches,
                       "note": "reference arithmetic (fp32 MACs x 2) / time / measured dense-bf16 peak; the kernel issues 3 "
                               "FP16 tensor passes per product to keep fp32 accuracy, after folding the bottleneck layer"})
-        if t:
+        if t and k not in ("encode_prop", "encode_nerf", "color_mlp"):
+            # two launches of different size per chunk (one per level): quote the limiter, not a per-launch traffic figure
+            e["traffic"] = None
+            e["bound"] = t.get("bound", "unknown")
+            e["limiter_pct"] = t.get("limiter_pct")
+        elif t:
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
             # per-launch DRAM bytes of the captured launch, scaled to this run's average launch size
             scale = (n * steps / launches) / t.get("rays_per_launch", tj.get("chunk_rays", 131072))

@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--workload", default="eval_800x600_waymo_gin")
     ap.add_argument("--extras", default="default", help="'default', 'none', 'all' or a comma list of: "
                     + ",".join(sorted(set(EXTRAS_1 + EXTRAS_N))))
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused NVLink tile exchange (default) "
+                    "or render + NCCL all-gather")
     ap.add_argument("--chunk-rays", type=int, default=0)
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -385,10 +387,25 @@ def run_ours(args):
     per, start, stop = R.shard_bounds(world * n, world, rank)
     assert per == n and stop - start == n
 
-    def step():
+    peer = None
+    if world > 1 and args.gather == "peer":
+        from ucnerf_b200.peer import PeerImage
+        try:
+            peer = PeerImage(world * n, device=dev)          # collective; every rank falls back together
+        except _lib.UcnerfError as e:
+            if rank == 0:
+                print(f"[bench] peer exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+
+    def step_nccl():
         out = r.render_rays(rays_d, 1.0, rays_d["rand_vec"], ("packed",))
         img = R.gather_tiles(out["packed"], world, world * n)
         return out, img
+
+    def step_peer():    # the tile exchange fused into the compositing kernel (NVLink peer stores) + one 4-byte all-reduce
+        img, _ = peer.render(r, rays_d, 1.0, rays_d["rand_vec"], start)
+        return {"packed": img[start:stop]}, img
+
+    step = step_peer if peer is not None else step_nccl
 
     # ---- timed region: device-resident inputs -------------------------------------------------
     for _ in range(args.warmup):
@@ -411,6 +428,10 @@ def run_ours(args):
     r.set_option("timing", 0)
     clocks = ck.result
     packed_dev = out_dev["packed"].clone()
+    # N > 1: the same step with the other exchange, for the record (not the headline)
+    other_ms = None
+    if world > 1 and peer is not None:
+        other_ms = timed(cx, step_nccl, args.steps, 2) / args.steps
 
     # ---- end-to-end: host buffers through the C-ABI host entry --------------------------------
     pin = {k: v.reshape(-1).contiguous().pin_memory() if k in ("radii", "near", "far") else v.contiguous().pin_memory()
@@ -424,11 +445,14 @@ def run_ours(args):
         pin2 = {k: (v if v.dim() == 2 else v.reshape(-1, 1)) for k, v in pin.items()}
         dev_in = {k: torch.empty_like(v, device=dev) for k, v in pin2.items()}
 
-        def e2e_step():     # host rays in -> device render -> the ONE all-gather -> this rank's rows of the image back
+        def e2e_step():     # host rays in -> device render + tile exchange -> this rank's rows of the image back
             for k in dev_in:
                 dev_in[k].copy_(pin2[k], non_blocking=True)
-            o = r.render_rays(dev_in, 1.0, dev_in["rand_vec"], ("packed",))
-            img = R.gather_tiles(o["packed"], world, world * n)
+            if peer is not None:
+                img, _ = peer.render(r, dev_in, 1.0, dev_in["rand_vec"], start)
+            else:
+                o = r.render_rays(dev_in, 1.0, dev_in["rand_vec"], ("packed",))
+                img = R.gather_tiles(o["packed"], world, world * n)
             out_h["packed"].copy_(img[start:stop], non_blocking=True)
             torch.cuda.current_stream().synchronize()
     with Clocks(rank, local) as ck:
@@ -536,7 +560,10 @@ def run_ours(args):
                        "samples_per_ray": spr, "prop_samples": wl.num_prop_samples, "nerf_samples": wl.num_nerf_samples,
                        "grid_levels": [wl.grid_levels(d) for d in wl.prop_desired] + [wl.grid_levels(wl.nerf_desired)],
                        "log2_hashmap_size": wl.log2_hashmap_size, "parallelism": f"ray-tile x{world}, replicated model",
-                       "collective": "render.gather_tiles: 1 all_gather of packed [rays,12] per step" if world > 1 else "none",
+                       "collective": ("none" if world == 1 else
+                                      "fused: compositing kernel stores the packed tiles into every rank's image over NVLink "
+                                      "peer memory (peer.PeerImage) + one 4-byte all_reduce per step" if peer is not None else
+                                      "render.gather_tiles: 1 all_gather of packed [rays,12] per step"),
                        "l2": "working set (330 MB hash tables + >0.5 GB per-chunk workspace) exceeds the 126 MB L2; "
                              "no explicit flush"},
             "rays_per_sec": value / spr,
@@ -551,6 +578,9 @@ def run_ours(args):
                                        "note": "algorithmic bytes of both gather kernels / their summed time (BASELINE.md section 4)"},
             "clocks": clocks, "checksum_mean_rgb": checksum,
         }
+        if other_ms is not None:
+            line["nccl_all_gather_variant"] = {"ms_per_step": other_ms, "value": world * n * spr / (other_ms * 1e-3),
+                                               "note": "same step with render + render.gather_tiles (NCCL all-gather of 48 B/ray)"}
         line.update(line_extra)
         if world == 1 and (extras & {"cpu_baseline", "parity"}):
             cpu = CpuReference(wl, sd)
@@ -574,6 +604,8 @@ def run_ours(args):
         line["bench_wall_s"] = time.perf_counter() - t_start
         print(json.dumps(line), flush=True)
     if world > 1:
+        if peer is not None:
+            peer.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -301,6 +301,23 @@ int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value);
  * off.  The sky branch of that code (model_sky=True) is not part of the fused path. */
 int ucnerf_set_rgb_affine(ucnerf_model* m, const float* affine12_host);
 
+/* ---- fused tile exchange over NVLink peer memory ----
+ * Multi-GPU render without a trailing all-gather: while peer targets are set, the compositing kernel of the final level
+ * stores every finished packed row [12 floats, layout of ucnerf_outputs.packed] of ray i of the call into
+ * peer_images[k] + 12 * (row0 + i) for k < n_peers - the image buffers of all ranks (this rank's own included), peer
+ * ones mapped with ucnerf_peer_open.  n_peers = 0 switches it off.  The caller orders frame completion across ranks
+ * (one tiny all-reduce after the render, ucnerf_b200/peer.py).  The reference instead gathers every leaf of every
+ * 15k-ray chunk with accelerate.gather (models.py:L965-968). */
+#define UCNERF_MAX_PEERS 16
+int ucnerf_set_peer_targets(ucnerf_model* m, uint32_t n_peers, void* const* peer_images, uint64_t row0);
+
+/* Image buffers for that exchange: plain device allocations with a 64-byte IPC handle the owner sends to its peers
+ * (alloc / free on the owner, open / close on a peer; zero-initialised). */
+int ucnerf_peer_alloc(uint64_t bytes, void** dptr_out, uint8_t* handle64_out);
+int ucnerf_peer_open(const uint8_t* handle64, void** dptr_out);
+int ucnerf_peer_close(void* dptr);
+int ucnerf_peer_free(void* dptr);
+
 /* ---- sky head on tensor cores ----
  * Replaces models.py:L326-337: ray_batch = [origins, directions, near = far, far = 1.5 far[0], cam_dirs] ->
  * render_rays(network_fn = skynerf) -> rgb_map (models.py:L743-904: NeRF D=8 W=256 raw-xyz input, skip after layer 4,

@@ -147,6 +147,28 @@ def main():
         ref = R.render_image(None, One(), b2d, False, 1.0, Cfg(), renderer=r, rand_vec=rv)
         for k in ("rgb", "depth", "acc", "distance_mean", "distance_median"):
             assert torch.equal(img[k], ref[k]), k
+        # `img` came through the fused NVLink tile exchange (peer.PeerImage, the default on NCCL); the plain all-gather
+        # path must give the same image, and so must several frames in a row (the two image buffers alternate)
+        assert getattr(r, "_peer_image", None) is not None and r._peer_image[1] is not None, "peer exchange not active"
+
+        class NoPeer(Cfg):
+            ucnerf_peer_exchange = False
+
+        img_nccl = R.render_image(None, Acc(), b2d, False, 1.0, NoPeer(), renderer=r, rand_vec=rv, return_weights=True)
+        img_peer = R.render_image(None, Acc(), b2d, False, 1.0, Cfg(), renderer=r, rand_vec=rv, return_weights=True)
+        for k in ("rgb", "depth", "acc", "distance_percentile_95", "weights", "coord"):
+            assert torch.equal(img_peer[k], img_nccl[k]), k
+        for k in ("rgb", "depth", "acc", "distance_percentile_95"):
+            assert torch.equal(img_nccl[k], ref[k]), k
+        rays2 = O.synthetic_rays(H * W, seed=78)
+        b2 = {k: v.reshape(H, W, -1).cuda() for k, v in rays2.items()}
+        for frame in range(3):
+            got = R.render_image(None, Acc(), b2 if frame % 2 else b2d, False, 1.0, Cfg(), renderer=r,
+                                 rand_vec=(b2 if frame % 2 else b2d)["rand_vec"].reshape(-1, 3))
+            want = R.render_image(None, One(), b2 if frame % 2 else b2d, False, 1.0, Cfg(), renderer=r,
+                                  rand_vec=(b2 if frame % 2 else b2d)["rand_vec"].reshape(-1, 3))
+            assert torch.equal(got["rgb"], want["rgb"]) and torch.equal(got["acc"], want["acc"]), frame
+        r._peer_image[1].close()
     dist.barrier()
     if rank == 0:
         print("DIST_OK", a.backend, world)

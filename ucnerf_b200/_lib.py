@@ -98,7 +98,8 @@ EXPORTS = [
     "ucnerf_grad_total_variation", "ucnerf_model_create", "ucnerf_model_refresh", "ucnerf_model_destroy",
     "ucnerf_render_rays", "ucnerf_render_rays_host", "ucnerf_launch_count", "ucnerf_set_option",
     "ucnerf_get_timing", "ucnerf_generate_rays", "ucnerf_render_camera", "ucnerf_render_camera_host",
-    "ucnerf_set_rgb_affine", "ucnerf_sky_create", "ucnerf_sky_destroy", "ucnerf_sky_render",
+    "ucnerf_set_rgb_affine", "ucnerf_set_peer_targets", "ucnerf_peer_alloc", "ucnerf_peer_open", "ucnerf_peer_close",
+    "ucnerf_peer_free", "ucnerf_sky_create", "ucnerf_sky_destroy", "ucnerf_sky_render",
     "ucnerf_grid_adam_step", "ucnerf_grid_adam_step_clipped", "ucnerf_grid_table_stats",
     "ucnerf_pooled_encode_forward",
     "ucnerf_pooled_encode_backward",
@@ -144,6 +145,11 @@ def load():
     lib.ucnerf_render_camera.argtypes = [vp, C.POINTER(Camera), u32, u32, C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_render_camera_host.argtypes = [vp, C.POINTER(Camera), u32, u32, C.c_double, C.POINTER(Outputs), vp]
     lib.ucnerf_set_rgb_affine.argtypes = [vp, vp]
+    lib.ucnerf_set_peer_targets.argtypes = [vp, u32, C.POINTER(vp), C.c_uint64]
+    lib.ucnerf_peer_alloc.argtypes = [C.c_uint64, C.POINTER(vp), C.c_char_p]
+    lib.ucnerf_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.ucnerf_peer_close.argtypes = [vp]
+    lib.ucnerf_peer_free.argtypes = [vp]
     lib.ucnerf_grid_adam_step.argtypes = [vp, vp, vp, vp, vp, u32, u32, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_uint64, C.c_double, C.c_int, vp]
     lib.ucnerf_grid_adam_step_clipped.argtypes = [vp, vp, vp, vp, vp, u32, u32, C.c_double, C.c_double, C.c_double,

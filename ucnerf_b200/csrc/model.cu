@@ -82,6 +82,9 @@ struct ucnerf_model {
     int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 FP16 split (error if shapes unsupported), 2 = auto
     bool use_affine = false;
     float affine[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};   // BrightnessCorrection affine of the current image (row-major 3x4)
+    uint32_t n_peers = 0;                 // fused tile exchange (ucnerf_set_peer_targets)
+    float* peer_images[UCNERF_MAX_PEERS] = {};
+    uint64_t peer_row0 = 0;
     int encode_runs = 0;  // cell-run reuse in sample_encode_kernel (bit 0 = proposal levels, bit 1 = NeRF level): measured
                           // slower on B200 (profiles/r1_summary.md), kept as an option
     int warp_rays_log2[2] = {5, 5};  // sample_encode_kernel warp shape {proposal levels, NeRF level}: 2^k rays x 2^(5-k) samples
@@ -418,7 +421,10 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
             cq.o_p5 = o.distance_percentile_5 ? o.distance_percentile_5 + ray0 : nullptr;
             cq.o_p95 = o.distance_percentile_95 ? o.distance_percentile_95 + ray0 : nullptr;
             cq.o_packed = o.packed ? o.packed + 12 * ray0 : nullptr;
-            cq.extras = (cq.o_mean || cq.o_median || cq.o_p5 || cq.o_p95 || cq.o_packed) ? 1 : 0;
+            cq.n_peers = (int)m->n_peers;
+            for (uint32_t k = 0; k < m->n_peers; ++k) cq.peer_packed[k] = m->peer_images[k];
+            cq.peer_row0 = m->peer_row0 + ray0;
+            cq.extras = (cq.o_mean || cq.o_median || cq.o_p5 || cq.o_p95 || cq.o_packed || cq.n_peers) ? 1 : 0;
             cq.use_affine = m->use_affine ? 1 : 0;
             std::memcpy(cq.affine, m->affine, sizeof(cq.affine));
         } else {
@@ -499,6 +505,20 @@ extern "C" int ucnerf_set_rgb_affine(ucnerf_model* m, const float* affine12_host
     std::lock_guard<std::mutex> lk(m->mu);
     m->use_affine = affine12_host != nullptr;
     if (affine12_host) std::memcpy(m->affine, affine12_host, sizeof(m->affine));
+    return 0;
+}
+
+extern "C" int ucnerf_set_peer_targets(ucnerf_model* m, uint32_t n_peers, void* const* peer_images, uint64_t row0) {
+    UC_REQUIRE(m, "set_peer_targets: null model");
+    UC_REQUIRE(n_peers <= UCNERF_MAX_PEERS, "set_peer_targets: too many peers");
+    UC_REQUIRE(n_peers == 0 || peer_images, "set_peer_targets: null peer list");
+    std::lock_guard<std::mutex> lk(m->mu);
+    for (uint32_t k = 0; k < n_peers; ++k) {
+        UC_REQUIRE(peer_images[k], "set_peer_targets: null peer image");
+        m->peer_images[k] = static_cast<float*>(peer_images[k]);
+    }
+    m->n_peers = n_peers;
+    m->peer_row0 = row0;
     return 0;
 }
 

@@ -305,6 +305,13 @@ composite_kernel(const CompositeParams p) {
             o[1] = make_float4(ro.acc, ro.dist_mean, ro.dist_median, ro.dist_p5);
             o[2] = make_float4(ro.dist_p95, ro.depth_raw, 0.f, 0.f);
         }
+        // fused tile exchange: the finished row goes to every rank's image (posted stores over NVLink for the peers)
+        for (int k = 0; k < p.n_peers; ++k) {
+            float4* o = reinterpret_cast<float4*>(p.peer_packed[k] + 12 * ((size_t)p.peer_row0 + ray));
+            o[0] = make_float4(ro.rgb[0], ro.rgb[1], ro.rgb[2], ro.depth);
+            o[1] = make_float4(ro.acc, ro.dist_mean, ro.dist_median, ro.dist_p5);
+            o[2] = make_float4(ro.dist_p95, ro.depth_raw, 0.f, 0.f);
+        }
     }
 }
 

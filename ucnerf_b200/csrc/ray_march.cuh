@@ -115,6 +115,9 @@ struct CompositeParams {
     float* weights;          // [N, S]
     // optional per-ray outputs (NULL = skip)
     float *o_rgb, *o_depth, *o_depth_raw, *o_acc, *o_mean, *o_median, *o_p5, *o_p95, *o_packed;
+    int n_peers;             // fused tile exchange: the packed row also goes to peer_packed[k] + 12 * (peer_row0 + ray)
+    float* peer_packed[16];  // image buffers of all ranks (NVLink peer mappings + this rank's own), see peer.cu
+    uint64_t peer_row0;
     int use_affine;          // final level only: rgb <- A rgb + t (BrightnessCorrection, models.py:L339-363)
     float affine[12];        // row-major [3][4]
 };

@@ -455,6 +455,29 @@ def gather_tiles(tile: torch.Tensor, world: int, num_rows: Optional[int] = None)
     return full if num_rows is None else full[:num_rows]
 
 
+def _peer_image(r, world, per, config):
+    """The PeerImage (fused NVLink tile exchange, ucnerf_b200/peer.py) cached on the renderer, or None when it is switched
+    off / not applicable (CPU stand-in renderer, non-NCCL backend) / not available (no peer access): then the plain
+    all-gather path runs.  Creating it is collective, and so is the fallback decision."""
+    if not getattr(config, "ucnerf_peer_exchange", True) or not hasattr(r, "_handle") or r.device.type != "cuda":
+        return None
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_backend() != "nccl":
+        return None
+    cached = getattr(r, "_peer_image", None)
+    if cached is not None and cached[0] == (world, per):
+        return cached[1]
+    from .peer import PeerImage
+    if cached is not None and cached[1] is not None:
+        cached[1].close()
+    try:
+        pi = PeerImage(world * per, device=r.device)
+    except _lib.UcnerfError:
+        pi = None
+    r._peer_image = ((world, per), pi)
+    return pi
+
+
 def _param_versions(module):
     """Fingerprint of a module's parameters: in-place updates (optimiser steps, load_state_dict) bump `_version`,
     re-assigned storage changes `data_ptr`."""
@@ -541,20 +564,29 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
     cand = cand[(cand < max(n_local, 1)) & (torch.arange(nv)[None, :] < ref_chunk)]
     pick = cand[torch.randperm(cand.numel())[:nv]].to(r.device)
     vis_want = [f"sdist_{l}" for l in range(nl)] + [f"weights_{l}" for l in range(nl)] + ["sample_rgb"]
+    # N > 1 on NVLink-connected GPUs: the tile exchange is fused into the compositing kernel (peer.PeerImage) unless the
+    # sky head still has to blend into the pixels afterwards or `config.ucnerf_peer_exchange = False`
+    peer = _peer_image(r, world, per, config) if (world > 1 and not use_sky) else None
+    peer_img = None
     try:
-        out = r.render_rays(local, train_frac, lrv, want)
+        if peer is not None:
+            peer_img, out = peer.render(r, local, train_frac, lrv, rank * per, [w for w in want if w != "packed"])
+        else:
+            out = r.render_rays(local, train_frac, lrv, want)
         vis = r.render_rays({k: v[pick] for k, v in local.items()}, train_frac, lrv[pick], vis_want)
     finally:
         if affine is not None:
             r.set_rgb_affine(None)   # the affine belongs to this image only, also when the render raises
-    packed = out["packed"]
+    packed = out["packed"] if peer_img is None else None
     sky_rgbs = None
     if use_sky:
         sky_rgbs = _sky_head(m, local, config)
         if affine_sky is not None:  # models.py:L353-354
             sky_opacity = 1 - torch.sum(out[f"weights_{nl - 1}"], dim=-1, keepdim=True)
             packed[:, 0:3] += sky_opacity * (sky_rgbs @ affine_sky[:3, :3].T + affine_sky[:3, 3])
-    if world > 1:
+    if peer_img is not None:
+        packed = peer_img[:num_rays].clone()                # every rank's tile is already here (the buffer is reused 2 frames on)
+    elif world > 1:
         packed = gather_tiles(packed, world, num_rays)      # the ONE collective per image
         if sky_rgbs is not None:
             sky_rgbs = gather_tiles(sky_rgbs, world, num_rays)

@@ -301,6 +301,27 @@ int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value);
  * off.  The sky branch of that code (model_sky=True) is not part of the fused path. */
 int ucnerf_set_rgb_affine(ucnerf_model* m, const float* affine12_host);
 
+/* ---- fp32-accurate tensor-core GEMMs for the training step's dense layers (csrc/gemm3_tc.cu) ----
+ * Replace the cuBLAS fp32 SGEMMs that nn.Linear runs for the reference's MLPs (internal/models.py:L438-441, L475-483,
+ * L643-652) and their autograd: tcgen05 kind::tf32 with the 3xTF32 split (hi*hi + lo*hi + hi*lo, fp32 accumulate in
+ * TMEM), ~2^-21 relative error per product, no operand scaling.  All matrices are device fp32, row-major.
+ *   ucnerf_gemm_nt: C[M,N] = sum_s A_s[M,k_s] B_s[N,k_s]^T (+ bias[N]) (relu)   N <= 256, sum of ceil(k_s / 32) <= 24
+ *                   forward y = [x_0 | x_1 | ..] W^T + b with B_s = W[:, cols of segment s] (ldb = W's row length),
+ *                   input gradient dx_s = dy W_s with B = W_s^T
+ *   ucnerf_gemm_tn: C[N1,N2] += A[M,N1]^T B[M,N2]   (reduction over the M rows; C initialised by the caller)
+ *                   weight gradient dW_s = dy^T x_s
+ * ucnerf_gemm_status: 0, or 5 (+ ucnerf_last_error) when a kernel's pipeline watchdog fired. */
+typedef struct ucnerf_gemm_seg {
+    const float* a;   /* [M, k]  rows lda apart */
+    const float* b;   /* [N, k]  rows ldb apart */
+    uint32_t lda, ldb, k;
+} ucnerf_gemm_seg;
+int ucnerf_gemm_nt(uint32_t M, uint32_t N, uint32_t nseg, const ucnerf_gemm_seg* segs, const float* bias, int relu, float* C,
+                   uint32_t ldc, void* stream);
+int ucnerf_gemm_tn(uint32_t M, uint32_t N1, uint32_t N2, const float* A, uint32_t lda, const float* B, uint32_t ldb, float* C,
+                   uint32_t ldc, void* stream);
+int ucnerf_gemm_status(uint32_t* out32);
+
 /* ---- fused tile exchange over NVLink peer memory ----
  * Multi-GPU render without a trailing all-gather: while peer targets are set, the compositing kernel of the final level
  * stores every finished packed row [12 floats, layout of ucnerf_outputs.packed] of ray i of the call into

@@ -67,6 +67,15 @@ load_inverted('ucnerf_b200.gridencoder.pooled', ROOT + '/ucnerf_b200/gridencoder
 load_inverted('ucnerf_b200.stepfun', ROOT + '/ucnerf_b200/stepfun.py')
 load_inverted('ucnerf_b200.render_train', ROOT + '/ucnerf_b200/render_train.py')
 
+# the tensor-core dense layers (ucnerf_b200.gemm.tc_linear, CUDA only) are served by torch's own fp32 linear here: the
+# rehearsal covers the wiring of _mlp_forward_native (segments instead of torch.cat), tests/test_gpu_gemm.py the kernels
+import torch as _torch
+import ucnerf_b200.gemm as _G
+def _tc_linear_cpu(xs, weight, bias=None, relu=False):
+    y = _torch.nn.functional.linear(_torch.cat(list(xs), dim=-1), weight, bias)
+    return _torch.relu(y) if relu else y
+_G.tc_linear = _tc_linear_cpu
+
 import pytest
 import re
 NOT_EXERCISED = []

@@ -89,7 +89,8 @@ def test_unsupported_configurations_raise_before_any_kernel():
 
 
 @pytest.mark.gpu
-def test_level_loop_matches_the_reference_training_forward_and_backward():
+@pytest.mark.parametrize("native_mlp", [True, False], ids=["tensor-core layers", "nn.Linear layers"])
+def test_level_loop_matches_the_reference_training_forward_and_backward(native_mlp):
     from ucnerf_b200.train_forward import level_loop
     g = load_golden("train_forward")
     cfg, params, batch = cases.make_case("waymo", g["target"].shape[0])
@@ -100,7 +101,8 @@ def test_level_loop_matches_the_reference_training_forward_and_backward():
     b = {k: v.cuda() for k, v in batch.items() if k != "rand_vec"}
     draws = [{k: torch.from_numpy(g[f"draw{l}_{k}"]).cuda() for k in ("jitter01", "flip01", "rot01", "rand_vec")}
              for l in range(cfg.num_levels)]
-    renderings, ray_history = level_loop(model, True, b, float(g["train_frac"]), compute_extras=False, draws=draws)
+    renderings, ray_history = level_loop(model, True, b, float(g["train_frac"]), compute_extras=False, draws=draws,
+                                         native_mlp=native_mlp)
     assert model.training
     target = torch.from_numpy(g["target"]).cuda()
     Gs = [torch.from_numpy(g[f"G{l}"]).cuda() for l in range(cfg.num_levels)]

@@ -4,8 +4,9 @@ native ops of this package, returning the reference's `(renderings, ray_history)
     renderings, ray_history = level_loop(model, rand, batch, train_frac, compute_extras=False)
 
 `model` is the reference's own `Model` (or any module tree with the same attribute / parameter names): its
-hyper-parameters are read as attributes, its `nn.Linear` layers are called as they are (cuBLAS), and everything between
-them runs in libucnerf_b200.so:
+hyper-parameters are read as attributes, the weights of its `nn.Linear` layers feed fp32-accurate tensor-core GEMMs
+(gemm.tc_linear; `native_mlp=False` calls the modules themselves, i.e. cuBLAS), and everything between them runs in
+libucnerf_b200.so as well:
 
     resampling incl. dilation + jitter       stepfun.resample_level        (models.py:L156-205)
     render.cast_rays, rand pattern            render_train.cast_rays        (L208-217, render.py:L94-152)
@@ -76,8 +77,46 @@ def _pos_enc(x, max_deg):
     return torch.cat([x, torch.sin(torch.cat([xb, xb + 0.5 * torch.pi], dim=-1))], dim=-1)
 
 
-def _mlp_forward(mlp, rand, means, stds, viewdirs, merge_runs=True):
+def _native_mlp_ok(mlp):
+    """The tensor-core layers (ucnerf_b200.gemm.tc_linear) cover widths up to 256 and the default layer layout."""
+    if mlp.density_layer[0].out_features > 256 or mlp.density_layer[2].out_features > 256:
+        return False
+    if getattr(mlp, "disable_rgb", False):
+        return True
+    return (mlp.net_depth_viewdirs == 2 and mlp.skip_layer_dir == 0 and mlp.net_width_viewdirs <= 256
+            and mlp.bottleneck_width <= 256 and 3 + 6 * mlp.deg_view <= 256)
+
+
+def _mlp_forward_native(mlp, rand, means, stds, viewdirs, merge_runs=True):
+    """MLP.forward (models.py:L514-685) with every dense layer on the tensor cores (gemm.tc_linear: 3xTF32, fp32 accuracy,
+    forward and backward) instead of nn.Linear's cuBLAS SGEMMs; the reference's `torch.cat` copies become K segments."""
+    from .gemm import tc_linear
+    features, coord = pooled_encode(mlp.encoder, means, stds, merge_runs=merge_runs)   # L487-496, L512
+    d0, d2 = mlp.density_layer[0], mlp.density_layer[2]
+    x = tc_linear([tc_linear([features], d0.weight, d0.bias, relu=True)], d2.weight, d2.bias)   # L507
+    raw_density = x[..., 0]                                                       # L508
+    if rand and getattr(mlp, "density_noise", 0.) > 0:                            # L510-511
+        raw_density = raw_density + mlp.density_noise * torch.randn_like(raw_density)
+    density = F.softplus(raw_density + mlp.density_bias)                          # L581
+    if getattr(mlp, "disable_rgb", False):
+        return dict(coord=coord, density=density, rgb=None)
+    bottleneck = x                                                                # L601
+    if rand and getattr(mlp, "bottleneck_noise", 0.) > 0:                         # L604-605
+        bottleneck = bottleneck + mlp.bottleneck_noise * torch.randn_like(bottleneck)
+    dir_enc = _pos_enc(viewdirs, mlp.deg_view)                                    # L620-627
+    dir_enc = torch.broadcast_to(dir_enc[..., None, :], bottleneck.shape[:-1] + (dir_enc.shape[-1],)).contiguous()
+    l0, l1 = mlp.lin_second_stage_0, mlp.lin_second_stage_1
+    y0 = tc_linear([bottleneck, dir_enc], l0.weight, l0.bias, relu=True)          # L643-647, i = 0 (then cat with inputs)
+    y1 = tc_linear([y0, bottleneck, dir_enc], l1.weight, l1.bias, relu=True)      # i = 1
+    rgb = torch.sigmoid(mlp.rgb_premultiplier * tc_linear([y1], mlp.rgb_layer.weight, mlp.rgb_layer.bias) + mlp.rgb_bias)
+    rgb = rgb * (1 + 2 * mlp.rgb_padding) - mlp.rgb_padding                       # L665
+    return dict(coord=coord, density=density, rgb=rgb)
+
+
+def _mlp_forward(mlp, rand, means, stds, viewdirs, merge_runs=True, native_mlp=True):
     """MLP.forward (models.py:L514-685) for the supported configuration; predict_density's front end is the fused op."""
+    if native_mlp and _native_mlp_ok(mlp):
+        return _mlp_forward_native(mlp, rand, means, stds, viewdirs, merge_runs)
     features, coord = pooled_encode(mlp.encoder, means, stds, merge_runs=merge_runs)   # L487-496, L512
     x = mlp.density_layer(features)                                               # L507
     raw_density = x[..., 0]                                                       # L508
@@ -112,14 +151,15 @@ def _hash_decay(encoder):
 
 
 def level_loop(model, rand, batch, train_frac, compute_extras=False, hash_decay=True, generator=None, draws=None,
-               merge_runs='auto'):
+               merge_runs='auto', native_mlp=True):
     """-> (renderings, ray_history), the lists Model.forward builds in its level loop.  `draws` (optional): one dict per
     level with the uniform / normal draws `jitter01`, `flip01`, `rot01`, `rand_vec` (testing / reproducibility); else
     they are drawn on the device with `generator`, in the reference's order.  `merge_runs`: backward variant of the
     pooled encode (False / True / 'ray', see gridencoder.pooled.pooled_encode); 'auto' = the measured best per level:
     'ray' on the proposal levels, True on the NeRF level.  `hash_decay`: True = the reference's differentiable term
     (torch), 'fused' = its value from one native read pass without autograd (pair it with GridAdam(hash_decay_mult=...),
-    which applies the term's gradient inside the optimiser kernel), False = omit."""
+    which applies the term's gradient inside the optimiser kernel), False = omit.  `native_mlp`: dense layers on the
+    tensor cores (gemm.tc_linear, forward + backward) instead of the module's nn.Linear / cuBLAS calls."""
     _check_model(model, batch, compute_extras)
     lead = batch['origins'].shape[:-1]
     flat = lambda k, c: batch[k].reshape(-1, c)
@@ -159,7 +199,7 @@ def level_loop(model, rand, batch, train_frac, compute_extras=False, hash_decay=
             mlp = model.nerf_mlp
         _check_mlp(mlp)
         mr = ('ray' if is_prop else True) if merge_runs == 'auto' else merge_runs
-        ray_results = _mlp_forward(mlp, rand, means, stds, viewdirs, mr)          # L222-229
+        ray_results = _mlp_forward(mlp, rand, means, stds, viewdirs, mr, native_mlp)   # L222-229
         density, rgbs = ray_results['density'], ray_results['rgb']
         if scale_grads:                                                           # L232-234
             if rgbs is None:

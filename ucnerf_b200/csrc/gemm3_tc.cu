@@ -15,13 +15,19 @@
 //               canonical K-major SWIZZLE_128B layout (32 TF32 per 128-byte row) - bank-conflict-free mappings
 //   warps 8-11  epilogue: tcgen05.ld the accumulator (warp w owns TMEM lanes 32 (w % 4) ..), + bias, relu, store / red.add
 //   warp 12     one elected thread issues tcgen05.mma (M = 128, N <= 256, K = 8, kind::tf32) and tcgen05.commit
+//   warp 13     NT form: one elected thread streams the B operand (the layer's weights, split and swizzled ONCE per call
+//               by pack_b_kernel instead of once per 128-row tile) from L2 with cp.async.bulk onto the stage's mbarrier
 // 2-stage operand ring (96 KB per stage) with full / empty mbarriers; NT double-buffers the accumulator (2 x 256 TMEM
 // columns) so the drain of tile i overlaps the MMAs of tile i + 1.  Every mbarrier wait is bounded (watchdog ->
 // error code), as in the other tensor-core kernels.
 #include "../../include/ucnerf_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -39,7 +45,8 @@ constexpr int kStages = 2;
 constexpr uint32_t kSmemMisc = kStages * kStageBytes;      // 196608
 constexpr uint32_t kOffBar = 0, kOffTmem = 128, kOffBias = 256;
 constexpr uint32_t kSmemTotal = kSmemMisc + kOffBias + 1024 + 1024;   // + bias[256] + manual 1 KB alignment slack
-constexpr int kLoaderThreads = 256, kEpiWarp0 = 8, kMmaWarp = 12, kThreads = 13 * 32;
+constexpr int kLoaderThreads = 256, kEpiWarp0 = 8, kMmaWarp = 12, kCopyWarp = 13, kThreads = 14 * 32;
+constexpr uint32_t kBlobChunk = 2 * kBTile;                // packed weights: hi tile | lo tile per K chunk (64 KB)
 constexpr int kMaxChunks = 24;
 
 enum Bar { FULL0 = 0, FULL1, EMPTY0, EMPTY1, ACC_FULL0, ACC_FULL1, ACC_EMPTY0, ACC_EMPTY1, NUM_BARS };
@@ -82,6 +89,7 @@ struct NtParams {
     float* C;
     uint32_t ldc;
     uint32_t cvec;         // 1: rows of C are 16-byte aligned (float4 stores)
+    const uint8_t* bblob;  // packed B operand (pack_b_kernel): chunk c at c * kBlobChunk; NULL: the loaders split B per tile
     uint32_t* dbg;
 };
 
@@ -92,6 +100,8 @@ struct TnParams {
     float* C;
     uint32_t ldc;
     uint32_t chunks_per_cta;   // row chunks (32 rows) per CTA along grid.x
+    uint32_t mn_major;         // 1: MN-major operand tiles (no transposition), 0: transposing loader + K-major tiles
+    uint32_t veca, vecb;       // float4 loads allowed along the rows of A / B
     uint32_t* dbg;
 };
 
@@ -112,9 +122,8 @@ __device__ __forceinline__ void issue_stage(uint32_t stage_addr, uint32_t acc_ta
 // tile: row p / 8, piece p % 8; 8 consecutive threads cover one 128-byte row (coalesced, conflict-free stores).  All loads
 // of a thread are issued before the first split / store (PIECES = ceil(rows_total * 8 / 256) register-resident pieces).
 template <int PIECES>
-__device__ __forceinline__ void load_rowmajor_tile(uint8_t* hi_tile, uint32_t tile_bytes, const float* src, uint32_t ld,
-                                                   uint32_t rows_total, uint32_t rows_valid, uint32_t kvalid, bool vec, int t) {
-    float4 x[PIECES];
+__device__ __forceinline__ void fetch_rowmajor(float4 (&x)[PIECES], const float* src, uint32_t ld, uint32_t rows_total,
+                                               uint32_t rows_valid, uint32_t kvalid, bool vec, int t) {
 #pragma unroll
     for (int i = 0; i < PIECES; ++i) {
         const uint32_t p = t + kLoaderThreads * i, row = p >> 3, pc = p & 7;
@@ -131,6 +140,10 @@ __device__ __forceinline__ void load_rowmajor_tile(uint8_t* hi_tile, uint32_t ti
             }
         }
     }
+}
+template <int PIECES>
+__device__ __forceinline__ void store_kmajor(const float4 (&x)[PIECES], uint8_t* hi_tile, uint32_t tile_bytes, uint32_t rows_total,
+                                             int t) {
 #pragma unroll
     for (int i = 0; i < PIECES; ++i) {
         const uint32_t p = t + kLoaderThreads * i, row = p >> 3, pc = p & 7;
@@ -142,6 +155,13 @@ __device__ __forceinline__ void load_rowmajor_tile(uint8_t* hi_tile, uint32_t ti
             *reinterpret_cast<uint4*>(dst + tile_bytes) = lo;
         }
     }
+}
+template <int PIECES>
+__device__ __forceinline__ void load_rowmajor_tile(uint8_t* hi_tile, uint32_t tile_bytes, const float* src, uint32_t ld,
+                                                   uint32_t rows_total, uint32_t rows_valid, uint32_t kvalid, bool vec, int t) {
+    float4 x[PIECES];
+    fetch_rowmajor<PIECES>(x, src, ld, rows_total, rows_valid, kvalid, vec, t);
+    store_kmajor<PIECES>(x, hi_tile, tile_bytes, rows_total, t);
 }
 
 // TRANSPOSED load for the TN form: the tile's row index is a COLUMN n of the source, its K index a source ROW m.
@@ -179,6 +199,71 @@ __device__ __forceinline__ void load_transposed_tile(uint8_t* hi_tile, uint32_t 
     }
 }
 
+// MN-MAJOR tile for the TN form without any transposition: the reduction index K runs over source ROWS and the tile's
+// M / N index over source COLUMNS, which are contiguous in memory - the canonical MN-major layout of UMMA (instruction-
+// descriptor bits 15 / 16).  For 32-bit operands the only MN-major shared-memory layout is SWIZZLE_128B_BASE32B (layout
+// type 1; CUTLASS: Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> o (32 MN x 4 K):(1, 32)): atoms of 4 K-rows x 128 bytes
+// (32 MN elements), the 32-byte chunk index of a row XOR-ed with k % 4.  Atom (kb = k / 4, mb = mn / 32) sits at
+// (kb * (mn_total / 32) + mb) * 512: leading byte offset (next MN atom) 512, stride byte offset (next K atom)
+// mn_total / 32 * 512; a K = 8 MMA reads two K atoms.  Loads are float4 along the source row: as cheap as the K-major
+// loader of the NT form.
+template <int PIECES>
+__device__ __forceinline__ void fetch_mnmajor(float4 (&x)[PIECES], const float* src, uint32_t ld, uint32_t mn_total, uint32_t col0,
+                                              uint32_t cols_valid, uint32_t m0, uint32_t m_valid, bool vec, int t) {
+    const uint32_t ppr = mn_total >> 2;            // 16-byte pieces per K row
+#pragma unroll
+    for (int i = 0; i < PIECES; ++i) {
+        const uint32_t p = t + kLoaderThreads * i, k = p / ppr, mp = p - k * ppr;
+        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t col = col0 + 4 * mp, m = m0 + k;
+        if (k < 32 && m < m_valid && col < cols_valid) {
+            const float* g = src + (size_t)m * ld + col;
+            if (vec && col + 3 < cols_valid) {
+                x[i] = __ldg(reinterpret_cast<const float4*>(g));
+            } else {
+                x[i].x = __ldg(g);
+                if (col + 1 < cols_valid) x[i].y = __ldg(g + 1);
+                if (col + 2 < cols_valid) x[i].z = __ldg(g + 2);
+                if (col + 3 < cols_valid) x[i].w = __ldg(g + 3);
+            }
+        }
+    }
+}
+template <int PIECES>
+__device__ __forceinline__ void store_mnmajor(const float4 (&x)[PIECES], uint8_t* hi_tile, uint32_t tile_bytes, uint32_t mn_total,
+                                              int t) {
+    const uint32_t ppr = mn_total >> 2, atoms = mn_total >> 5;
+#pragma unroll
+    for (int i = 0; i < PIECES; ++i) {
+        const uint32_t p = t + kLoaderThreads * i, k = p / ppr, mp = p - k * ppr;
+        if (k < 32) {
+            uint4 hi, lo;
+            split_tf32(x[i].x, hi.x, lo.x); split_tf32(x[i].y, hi.y, lo.y); split_tf32(x[i].z, hi.z, lo.z); split_tf32(x[i].w, hi.w, lo.w);
+            uint8_t* dst = hi_tile + ((k >> 2) * atoms + (mp >> 3)) * 512 + (k & 3) * 128 + (((((mp & 7) >> 1) ^ (k & 3))) * 32) +
+                           (mp & 1) * 16;
+            *reinterpret_cast<uint4*>(dst) = hi;
+            *reinterpret_cast<uint4*>(dst + tile_bytes) = lo;
+        }
+    }
+}
+// shared-memory matrix descriptor, MN-major SWIZZLE_128B_BASE32B (layout type 1): LBO / SBO in 16-byte units
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) |
+           (1ull << 46) | (1ull << 61);
+}
+// 12 MMAs of one MN-major operand stage (A: 128 wide = 4 atoms, B: nb atoms)
+__device__ __forceinline__ void issue_stage_mn(uint32_t stage_addr, uint32_t acc_taddr, uint32_t idesc, bool first, uint32_t nb) {
+    const uint32_t a_hi = stage_addr, a_lo = a_hi + kATile, b_hi = a_lo + kATile, b_lo = b_hi + kBTile;
+#pragma unroll
+    for (int ks = 0; ks < kKC32 / 8; ++ks) {
+        const uint64_t dah = make_desc_mn(a_hi + ks * 4096, 32, 128), dal = make_desc_mn(a_lo + ks * 4096, 32, 128);
+        const uint64_t dbh = make_desc_mn(b_hi + ks * nb * 1024, 32, nb * 32), dbl = make_desc_mn(b_lo + ks * nb * 1024, 32, nb * 32);
+        umma_tf32(acc_taddr, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u);
+        umma_tf32(acc_taddr, dal, dbh, idesc, 1u);
+        umma_tf32(acc_taddr, dah, dbl, idesc, 1u);
+    }
+}
+
 struct Shared {
     uint8_t* smem;
     uint32_t bar0;
@@ -186,13 +271,13 @@ struct Shared {
     __device__ uint8_t* stage(int s) const { return smem + (size_t)s * kStageBytes; }
 };
 
-__device__ __forceinline__ Shared setup(uint8_t* smem_raw, int warp, uint32_t& tmem_base) {
+__device__ __forceinline__ Shared setup(uint8_t* smem_raw, int warp, uint32_t& tmem_base, uint32_t full_count = kLoaderThreads) {
     Shared sh;
     sh.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* misc = sh.smem + kSmemMisc;
     sh.bar0 = smem_u32(misc + kOffBar);
     if (threadIdx.x == 0) {
-        mbar_init(sh.bar(FULL0), kLoaderThreads); mbar_init(sh.bar(FULL1), kLoaderThreads);
+        mbar_init(sh.bar(FULL0), full_count); mbar_init(sh.bar(FULL1), full_count);
         mbar_init(sh.bar(EMPTY0), 1); mbar_init(sh.bar(EMPTY1), 1);
         mbar_init(sh.bar(ACC_FULL0), 1); mbar_init(sh.bar(ACC_FULL1), 1);
         mbar_init(sh.bar(ACC_EMPTY0), 128); mbar_init(sh.bar(ACC_EMPTY1), 128);
@@ -224,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_nt_kernel(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t tmem_base;
-    const Shared sh = setup(smem_raw, warp, tmem_base);
+    const Shared sh = setup(smem_raw, warp, tmem_base, kLoaderThreads + (p.bblob ? 1u : 0u));
     float* sBias = reinterpret_cast<float*>(sh.smem + kSmemMisc + kOffBias);
     for (int i = threadIdx.x; i < 256; i += kThreads) sBias[i] = (p.bias && i < (int)p.N) ? p.bias[i] : 0.f;
     __syncthreads();
@@ -240,10 +325,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_nt_kernel(const __grid_cons
             for (uint32_t c = 0; c < p.nchunks; ++c, ++k) {
                 const Chunk& ch = p.ch[c];
                 const int s = k & 1;
+                // the global loads do not need the stage: they are in flight while the MMAs of chunk k - 2 still read it
+                float4 xa[4];
+                fetch_rowmajor<4>(xa, ch.a + (size_t)row0 * ch.lda, ch.lda, 128, rows_valid, ch.kvalid, ch.veca != 0, t);
                 if (!mbar_wait(sh.bar(EMPTY0 + s), ((k >> 1) & 1) ^ 1, p.dbg, 1, EMPTY0 + s, tile, c)) goto done;
                 uint8_t* st = sh.stage(s);
-                load_rowmajor_tile<4>(st, kATile, ch.a + (size_t)row0 * ch.lda, ch.lda, 128, rows_valid, ch.kvalid, ch.veca != 0, t);
-                load_rowmajor_tile<8>(st + 2 * kATile, kBTile, ch.b, ch.ldb, p.npad, p.N, ch.kvalid, ch.vecb != 0, t);
+                store_kmajor<4>(xa, st, kATile, 128, t);
+                if (!p.bblob) load_rowmajor_tile<8>(st + 2 * kATile, kBTile, ch.b, ch.ldb, p.npad, p.N, ch.kvalid, ch.vecb != 0, t);
                 fence_proxy_async();
                 mbar_arrive(sh.bar(FULL0 + s));
             }
@@ -283,6 +371,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_nt_kernel(const __grid_cons
             tc_fence_before();
             mbar_arrive(sh.bar(ACC_EMPTY0 + acc));
         }
+    } else if (warp == kCopyWarp) {
+        // ================= B operand: bulk copies of the pre-packed weight chunks =================
+        if (lane == 0 && p.bblob) {
+            uint32_t k = 0;
+            const uint32_t bytes = p.npad * 128;
+            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (uint32_t c = 0; c < p.nchunks; ++c, ++k) {
+                    const int s = k & 1;
+                    if (!mbar_wait(sh.bar(EMPTY0 + s), ((k >> 1) & 1) ^ 1, p.dbg, 5, EMPTY0 + s, tile, c)) goto done;
+                    const uint32_t b_hi = smem_u32(sh.stage(s) + 2 * kATile);
+                    mbar_expect_tx(sh.bar(FULL0 + s), 2 * bytes);
+                    bulk_g2s(b_hi, p.bblob + (size_t)c * kBlobChunk, bytes, sh.bar(FULL0 + s));
+                    bulk_g2s(b_hi + kBTile, p.bblob + (size_t)c * kBlobChunk + kBTile, bytes, sh.bar(FULL0 + s));
+                }
+            }
+        }
     } else if (lane == 0) {
         // ================= MMA issuer =================
         uint32_t k = 0, it = 0;
@@ -312,20 +416,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_tn_kernel(const __grid_cons
     uint32_t tmem_base;
     const Shared sh = setup(smem_raw, warp, tmem_base);
     const uint32_t n1_0 = blockIdx.y * 128, n2_0 = blockIdx.z * 256;
-    const uint32_t n2 = min(256u, p.N2 - n2_0), npad2 = (n2 + 15) & ~15u;
+    const uint32_t n2 = min(256u, p.N2 - n2_0), npad2 = p.mn_major ? ((n2 + 31) & ~31u) : ((n2 + 15) & ~15u);
     const uint32_t total_chunks = (p.M + 31) / 32;
     const uint32_t c_begin = blockIdx.x * p.chunks_per_cta, c_end = min(c_begin + p.chunks_per_cta, total_chunks);
-    const uint32_t idesc = idesc_tf32(npad2);
+    const uint32_t idesc = idesc_tf32(npad2) | (p.mn_major ? ((1u << 15) | (1u << 16)) : 0u);
     if (c_begin >= c_end) goto done;   // (uniform per CTA)
 
     if (warp < 8) {
         uint32_t k = 0;
         for (uint32_t c = c_begin; c < c_end; ++c, ++k) {
             const int s = k & 1;
-            if (!mbar_wait(sh.bar(EMPTY0 + s), ((k >> 1) & 1) ^ 1, p.dbg, 11, EMPTY0 + s, c, 0)) goto done;
             uint8_t* st = sh.stage(s);
-            load_transposed_tile<16>(st, kATile, p.A, p.lda, 128, n1_0, p.N1, c * 32, p.M, warp, lane);
-            load_transposed_tile<16>(st + 2 * kATile, kBTile, p.B, p.ldb, npad2, n2_0, p.N2, c * 32, p.M, warp, lane);
+            if (p.mn_major) {
+                // the global loads do not need the stage: they are in flight while the MMAs of chunk k - 2 still read it
+                float4 xa[4], xb[8];
+                fetch_mnmajor<4>(xa, p.A, p.lda, 128, n1_0, p.N1, c * 32, p.M, p.veca != 0, threadIdx.x);
+                fetch_mnmajor<8>(xb, p.B, p.ldb, npad2, n2_0, p.N2, c * 32, p.M, p.vecb != 0, threadIdx.x);
+                if (!mbar_wait(sh.bar(EMPTY0 + s), ((k >> 1) & 1) ^ 1, p.dbg, 11, EMPTY0 + s, c, 0)) goto done;
+                store_mnmajor<4>(xa, st, kATile, 128, threadIdx.x);
+                store_mnmajor<8>(xb, st + 2 * kATile, kBTile, npad2, threadIdx.x);
+            } else {
+                if (!mbar_wait(sh.bar(EMPTY0 + s), ((k >> 1) & 1) ^ 1, p.dbg, 11, EMPTY0 + s, c, 0)) goto done;
+                load_transposed_tile<16>(st, kATile, p.A, p.lda, 128, n1_0, p.N1, c * 32, p.M, warp, lane);
+                load_transposed_tile<16>(st + 2 * kATile, kBTile, p.B, p.ldb, npad2, n2_0, p.N2, c * 32, p.M, warp, lane);
+            }
             fence_proxy_async();
             mbar_arrive(sh.bar(FULL0 + s));
         }
@@ -347,13 +461,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_tn_kernel(const __grid_cons
             }
         }
         tc_fence_before();
-    } else if (lane == 0) {
+    } else if (warp == kMmaWarp && lane == 0) {
         uint32_t k = 0;
         for (uint32_t c = c_begin; c < c_end; ++c, ++k) {
             const int s = k & 1;
             if (!mbar_wait(sh.bar(FULL0 + s), (k >> 1) & 1, p.dbg, 13, FULL0 + s, c, 0)) goto done;
             tc_fence_after();
-            issue_stage(smem_u32(sh.stage(s)), tmem_base, idesc, c == c_begin);
+            if (p.mn_major) issue_stage_mn(smem_u32(sh.stage(s)), tmem_base, idesc, c == c_begin, npad2 >> 5);
+            else issue_stage(smem_u32(sh.stage(s)), tmem_base, idesc, c == c_begin);
             umma_commit(sh.bar(EMPTY0 + s));
         }
         umma_commit(sh.bar(ACC_FULL0));
@@ -362,7 +477,33 @@ done:
     teardown(warp, tmem_base);
 }
 
+// B operand of the NT form (a layer's weights or their transpose), split into hi / lo TF32 and swizzled once per call:
+// block c writes K chunk c as [hi tile | lo tile] in the layout the MMA reads from shared memory.
+__global__ void __launch_bounds__(kLoaderThreads) pack_b_kernel(const __grid_constant__ NtParams p, uint8_t* __restrict__ blob) {
+    const Chunk& ch = p.ch[blockIdx.x];
+    load_rowmajor_tile<8>(blob + (size_t)blockIdx.x * kBlobChunk, kBTile, ch.b, ch.ldb, p.npad, p.N, ch.kvalid, ch.vecb != 0,
+                          threadIdx.x);
+}
+
 static uint32_t* g_dbg = nullptr;   // [32] words: watchdog record (0 = healthy)
+
+// packed-weight workspace per (device, stream): launches on one stream are ordered, different streams get their own
+static std::mutex g_blob_mu;
+static std::map<std::pair<int, void*>, uint8_t*> g_blobs;
+static int blob_for(void* stream, uint8_t** out) {
+    int dev = 0;
+    UC_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_blob_mu);
+    auto key = std::make_pair(dev, stream);
+    auto it = g_blobs.find(key);
+    if (it == g_blobs.end()) {
+        uint8_t* b = nullptr;
+        UC_CUDA_OK(cudaMalloc(&b, (size_t)kMaxChunks * kBlobChunk));
+        it = g_blobs.emplace(key, b).first;
+    }
+    *out = it->second;
+    return 0;
+}
 
 static int ensure_dbg() {
     if (!g_dbg) {
@@ -416,8 +557,16 @@ extern "C" int ucnerf_gemm_nt(uint32_t M, uint32_t N, uint32_t nseg, const ucner
         }
     }
     p.nchunks = nc;
-    UC_ENSURE_SMEM(kSmemTotal, gemm3_nt_kernel);
     const uint32_t ntiles = (M + 127) / 128;
+    static const int no_pack = getenv("UCNERF_GEMM_NO_PACK") ? atoi(getenv("UCNERF_GEMM_NO_PACK")) : 0;
+    if (!no_pack && ntiles > 1) {   // weights split + swizzled once per call, streamed by bulk copies
+        uint8_t* blob = nullptr;
+        if (int e = blob_for(stream, &blob)) return e;
+        pack_b_kernel<<<nc, kLoaderThreads, 0, (cudaStream_t)stream>>>(p, blob);
+        UC_LAUNCH_CHECK();
+        p.bblob = blob;
+    }
+    UC_ENSURE_SMEM(kSmemTotal, gemm3_nt_kernel);
     gemm3_nt_kernel<<<std::min<uint32_t>(ntiles, (uint32_t)kNumSMs), kThreads, kSmemTotal, (cudaStream_t)stream>>>(p);
     UC_LAUNCH_CHECK();
     return 0;
@@ -431,6 +580,12 @@ extern "C" int ucnerf_gemm_tn(uint32_t M, uint32_t N1, uint32_t N2, const float*
     if (int e = ensure_dbg()) return e;
     TnParams p{};
     p.M = M; p.N1 = N1; p.N2 = N2; p.A = A; p.B = B; p.lda = lda; p.ldb = ldb; p.C = C; p.ldc = ldc; p.dbg = g_dbg;
+    {
+        static const int force_transpose = getenv("UCNERF_GEMM_TN_TRANSPOSE") ? atoi(getenv("UCNERF_GEMM_TN_TRANSPOSE")) : 0;
+        p.mn_major = force_transpose ? 0u : 1u;
+    }
+    p.veca = (reinterpret_cast<uintptr_t>(A) % 16 == 0 && lda % 4 == 0) ? 1u : 0u;
+    p.vecb = (reinterpret_cast<uintptr_t>(B) % 16 == 0 && ldb % 4 == 0) ? 1u : 0u;
     const uint32_t t1 = (N1 + 127) / 128, t2 = (N2 + 255) / 256;
     const uint32_t total_chunks = (M + 31) / 32;
     uint32_t gx = std::max<uint32_t>(1u, (uint32_t)kNumSMs / (t1 * t2));

@@ -321,6 +321,9 @@ int ucnerf_gemm_nt(uint32_t M, uint32_t N, uint32_t nseg, const ucnerf_gemm_seg*
 int ucnerf_gemm_tn(uint32_t M, uint32_t N1, uint32_t N2, const float* A, uint32_t lda, const float* B, uint32_t ldb, float* C,
                    uint32_t ldc, void* stream);
 int ucnerf_gemm_status(uint32_t* out32);
+/* Backward glue of a dense layer in one pass: g[M,N] = gy * (y > 0) (y NULL: g = gy; g NULL: not written) and
+ * colsum[N] = column sums of g (the bias gradient; NULL: skipped).  Contiguous fp32 [M,N], N a multiple of 4 <= 1024. */
+int ucnerf_relu_mask_colsum(const float* gy, const float* y, float* g, float* colsum, uint32_t M, uint32_t N, void* stream);
 
 /* ---- fused tile exchange over NVLink peer memory ----
  * Multi-GPU render without a trailing all-gather: while peer targets are set, the compositing kernel of the final level

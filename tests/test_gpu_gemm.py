@@ -118,3 +118,18 @@ def test_errors():
         gemm.gemm_nt([(torch.zeros(4, 8, device="cuda"), torch.zeros(300, 8, device="cuda"))])      # N > 256
     with pytest.raises(RuntimeError, match="segment"):
         gemm.gemm_nt([(torch.zeros(4, 8, device="cuda"), torch.zeros(4, 9, device="cuda"))])
+
+
+@pytest.mark.parametrize("M,N", [(5000, 256), (262144, 64), (77, 4), (1000, 3)])
+def test_relu_mask_colsum(M, N):
+    from ucnerf_b200 import gemm
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    gy = torch.randn((M, N), device="cuda", generator=g)
+    y = torch.relu(torch.randn((M, N), device="cuda", generator=g))
+    got_g, got_s = gemm.relu_mask_colsum(gy, y)
+    ref_g = gy * (y > 0)
+    assert torch.equal(got_g, ref_g)
+    assert _rel(got_s, ref_g.double().sum(0)) < 1e-5
+    g2, s2 = gemm.relu_mask_colsum(gy, None)
+    assert g2 is gy or torch.equal(g2, gy)
+    assert _rel(s2, gy.double().sum(0)) < 1e-5

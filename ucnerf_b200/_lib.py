@@ -103,7 +103,7 @@ EXPORTS = [
     "ucnerf_render_rays", "ucnerf_render_rays_host", "ucnerf_launch_count", "ucnerf_set_option",
     "ucnerf_get_timing", "ucnerf_generate_rays", "ucnerf_render_camera", "ucnerf_render_camera_host",
     "ucnerf_set_rgb_affine", "ucnerf_set_peer_targets", "ucnerf_peer_alloc", "ucnerf_peer_open", "ucnerf_peer_close",
-    "ucnerf_peer_free", "ucnerf_gemm_nt", "ucnerf_gemm_tn", "ucnerf_gemm_status", "ucnerf_sky_create", "ucnerf_sky_destroy", "ucnerf_sky_render",
+    "ucnerf_peer_free", "ucnerf_gemm_nt", "ucnerf_gemm_tn", "ucnerf_gemm_status", "ucnerf_relu_mask_colsum", "ucnerf_sky_create", "ucnerf_sky_destroy", "ucnerf_sky_render",
     "ucnerf_grid_adam_step", "ucnerf_grid_adam_step_clipped", "ucnerf_grid_table_stats",
     "ucnerf_pooled_encode_forward",
     "ucnerf_pooled_encode_backward",
@@ -157,6 +157,7 @@ def load():
     lib.ucnerf_gemm_nt.argtypes = [u32, u32, u32, C.POINTER(GemmSeg), vp, C.c_int, vp, u32, vp]
     lib.ucnerf_gemm_tn.argtypes = [u32, u32, u32, vp, u32, vp, u32, vp, u32, vp]
     lib.ucnerf_gemm_status.argtypes = [C.POINTER(C.c_uint32)]
+    lib.ucnerf_relu_mask_colsum.argtypes = [vp, vp, vp, vp, u32, u32, vp]
     lib.ucnerf_grid_adam_step.argtypes = [vp, vp, vp, vp, vp, u32, u32, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_uint64, C.c_double, C.c_int, vp]
     lib.ucnerf_grid_adam_step_clipped.argtypes = [vp, vp, vp, vp, vp, u32, u32, C.c_double, C.c_double, C.c_double,

@@ -485,6 +485,47 @@ __global__ void __launch_bounds__(kLoaderThreads) pack_b_kernel(const __grid_con
                           threadIdx.x);
 }
 
+// Backward glue of a dense layer in ONE pass over the rows: g = gy * (y > 0) (the ReLU mask, relu'(pre) == (out > 0)) and
+// colsum[n] = sum_m g[m, n] (the bias gradient) - what autograd otherwise spreads over a compare, a multiply and a column
+// reduction (three reads + one write of the [M, N] tensor instead of two reads + one write).  y == NULL: no mask;
+// g == NULL: column sums only.  Thread = 4 consecutive columns (float4), rows strided over the grid.
+__global__ void __launch_bounds__(256) relu_mask_colsum_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                                               float* __restrict__ g, float* __restrict__ colsum, uint32_t M,
+                                                               uint32_t N, uint32_t rows_per_cta) {
+    const uint32_t n4 = (N + 3) >> 2;                      // float4 groups per row (N % 4 == 0 on this path)
+    const uint32_t tpr = n4;                               // threads per row
+    const uint32_t rpi = 256 / tpr;                        // rows per iteration
+    const uint32_t c4 = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
+    const uint32_t r0 = blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, M);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rsub < rpi) {
+        for (uint32_t r = r0 + rsub; r < r1; r += rpi) {
+            const size_t o = (size_t)r * N + 4 * c4;
+            float4 v = *reinterpret_cast<const float4*>(gy + o);
+            if (y) {
+                const float4 yy = *reinterpret_cast<const float4*>(y + o);
+                v.x = yy.x > 0.f ? v.x : 0.f; v.y = yy.y > 0.f ? v.y : 0.f; v.z = yy.z > 0.f ? v.z : 0.f; v.w = yy.w > 0.f ? v.w : 0.f;
+            }
+            if (g) *reinterpret_cast<float4*>(g + o) = v;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    if (colsum) {
+        __shared__ float4 sh[256];
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x < tpr) {
+            float4 t = sh[threadIdx.x];
+            for (uint32_t k = 1; k < rpi; ++k) {
+                const float4 u = sh[threadIdx.x + k * tpr];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            atomicAdd(colsum + 4 * threadIdx.x + 0, t.x); atomicAdd(colsum + 4 * threadIdx.x + 1, t.y);
+            atomicAdd(colsum + 4 * threadIdx.x + 2, t.z); atomicAdd(colsum + 4 * threadIdx.x + 3, t.w);
+        }
+    }
+}
+
 static uint32_t* g_dbg = nullptr;   // [32] words: watchdog record (0 = healthy)
 
 // packed-weight workspace per (device, stream): launches on one stream are ordered, different streams get their own
@@ -594,6 +635,22 @@ extern "C" int ucnerf_gemm_tn(uint32_t M, uint32_t N1, uint32_t N2, const float*
     gx = (total_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
     UC_ENSURE_SMEM(kSmemTotal, gemm3_tn_kernel);
     gemm3_tn_kernel<<<dim3(gx, t1, t2), kThreads, kSmemTotal, (cudaStream_t)stream>>>(p);
+    UC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ucnerf_relu_mask_colsum(const float* gy, const float* y, float* g, float* colsum, uint32_t M, uint32_t N,
+                                       void* stream) {
+    UC_REQUIRE(gy && (g || colsum), "relu_mask_colsum: null argument");
+    UC_REQUIRE(N >= 4 && N <= 1024 && N % 4 == 0, "relu_mask_colsum: N must be a multiple of 4 in [4, 1024]");
+    UC_REQUIRE(reinterpret_cast<uintptr_t>(gy) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(g) % 16 == 0, "relu_mask_colsum: tensors must be 16-byte aligned");
+    if (colsum) UC_CUDA_OK(cudaMemsetAsync(colsum, 0, sizeof(float) * N, (cudaStream_t)stream));
+    if (M == 0) return 0;
+    const uint32_t ctas = std::min<uint32_t>((uint32_t)kNumSMs * 8u, (M + 63) / 64);
+    const uint32_t rows_per_cta = (M + ctas - 1) / ctas;
+    relu_mask_colsum_kernel<<<(M + rows_per_cta - 1) / rows_per_cta, 256, 0, (cudaStream_t)stream>>>(gy, y, g, colsum, M, N,
+                                                                                                 rows_per_cta);
     UC_LAUNCH_CHECK();
     return 0;
 }

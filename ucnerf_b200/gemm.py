@@ -76,6 +76,26 @@ def status():
     _lib.check(_lib.load().ucnerf_gemm_status(buf), "gemm_status")
 
 
+def relu_mask_colsum(gy: torch.Tensor, y: Optional[torch.Tensor], want_g: bool = True, want_colsum: bool = True):
+    """One pass: g = gy * (y > 0) (y None: g is gy itself) and the column sums of g.  Returns (g, colsum)."""
+    M, N = gy.shape
+    if N % 4 != 0 or N > 1024 or M == 0:          # tiny / odd widths (rgb layer, proposal density): torch
+        g = gy if y is None else gy * (y > 0)
+        return g, (g.sum(dim=0) if want_colsum else None)
+    lib = _lib.load()
+    gy = _f32c(gy, "gy").contiguous()
+    g = torch.empty_like(gy) if (want_g and y is not None) else None
+    cs = torch.empty(N, device=gy.device, dtype=torch.float32) if want_colsum else None
+    if g is None and cs is None:
+        return gy, None
+    with torch.cuda.device(gy.device):
+        rc = lib.ucnerf_relu_mask_colsum(gy.data_ptr(), None if y is None else y.contiguous().data_ptr(),
+                                         None if g is None else g.data_ptr(), None if cs is None else cs.data_ptr(), M, N,
+                                         torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "relu_mask_colsum")
+    return (g if g is not None else gy), cs
+
+
 class _TcLinear(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -98,18 +118,15 @@ class _TcLinear(torch.autograd.Function):
     def backward(ctx, gy):
         weight, y, *x2 = ctx.saved_tensors
         offs = ctx.offs
-        g = gy.reshape(-1, weight.shape[0]).float()
-        if ctx.relu:
-            g = g * (y > 0)                      # relu'(pre-activation) == (output > 0)
-        g = g.contiguous()
         need = ctx.needs_input_grad            # (relu, weight, bias, *xs)
-        gw = gb = None
+        # relu'(pre-activation) == (output > 0); the mask and the bias gradient (column sums) in one pass over the rows
+        g, gb = relu_mask_colsum(gy.reshape(-1, weight.shape[0]).float().contiguous(), y if ctx.relu else None,
+                                 want_g=True, want_colsum=ctx.has_bias and need[2])
+        gw = None
         if need[1]:
             gw = torch.zeros_like(weight)
             for i, x in enumerate(x2):
                 gemm_tn(g, x, out=gw[:, offs[i]:offs[i + 1]])
-        if ctx.has_bias and need[2]:
-            gb = g.sum(dim=0)
         gxs = []
         for i, x in enumerate(x2):
             if need[3 + i]:

@@ -91,7 +91,52 @@ class Phases:
         return out
 
 
-def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", native_mlp="auto"):
+class SkyNet(torch.nn.Module):
+    """Module with the reference NeRF's attributes / parameter names (models.py:L743-795; D = 8, W = 256, skips = [4],
+    4-frequency view embedding) holding synthetic weights - the sky head `Model` builds with `Config.model_sky`."""
+
+    def __init__(self, heads):
+        super().__init__()
+        L = torch.nn.Linear
+        self.skips, self.use_viewdirs, self.embed_fn = [4], True, None
+        self.pts_linears = torch.nn.ModuleList([L(3, 256)] + [L(259 if i == 4 else 256, 256) for i in range(7)])
+        self.views_linears = torch.nn.ModuleList([L(283, 128)])
+        self.feature_linear, self.alpha_linear, self.rgb_linear = L(256, 256), L(256, 1), L(128, 3)
+        self.load_state_dict({k[len("skynerf."):]: v for k, v in heads.items() if k.startswith("skynerf.")})
+
+    @staticmethod
+    def embed_fn_view(v):            # get_embedder(4) (models.py:L689-727): [x, sin(x f), cos(x f)] for f = 1, 2, 4, 8
+        out = [v]
+        for f in (1.0, 2.0, 4.0, 8.0):
+            out += [torch.sin(v * f), torch.cos(v * f)]
+        return torch.cat(out, -1)
+
+    def forward(self, pts, views):   # NeRF.forward (models.py:L797-820) with nn.Linear: the cuBLAS arm of the A/B
+        v = self.embed_fn_view(views)
+        h = pts
+        for i, l in enumerate(self.pts_linears):
+            h = torch.relu(l(h))
+            if i in self.skips:
+                h = torch.cat([pts, h], -1)
+        alpha, feature = self.alpha_linear(h), self.feature_linear(h)
+        h = torch.relu(self.views_linears[0](torch.cat([feature, v], -1)))
+        return alpha, self.rgb_linear(h)
+
+
+def sky_torch(ray_batch, net, n_samples=120):
+    """models.render_rays + raw2outputs (models.py:L822-904) in plain torch on `net.forward` (reference semantics)."""
+    o, d, near, far, views = ray_batch[:, 0:3], ray_batch[:, 3:6], ray_batch[:, 6:7], ray_batch[:, 7:8], ray_batch[:, -3:]
+    t = torch.linspace(0., 1., steps=n_samples, device=o.device)
+    z = near * (1. - t) + 1. / far * t
+    pts = o[..., None, :] + d[..., None, :] * z[..., :, None]
+    alpha, rgb = net(pts, views.unsqueeze(1).expand(-1, n_samples, -1))
+    dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full_like(z[..., :1], 1e10)], -1) * torch.norm(d[..., None, :], dim=-1)
+    a = 1. - torch.exp(-torch.relu(alpha[..., 0]) * dists)
+    w = a * torch.cumprod(torch.cat([torch.ones_like(a[:, :1]), 1. - a + 1e-10], -1), -1)[:, :-1]
+    return {"rgb_map": torch.sum(w[..., None] * torch.sigmoid(rgb), -2)}
+
+
+def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", native_mlp="auto", sky=False):
     """One training step of config 5 timed on `dev` (process group already initialised when world > 1) -> result dict."""
     import torch.distributed as dist
     from ucnerf_b200 import _lib
@@ -103,6 +148,14 @@ def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", nati
     encoders = [m.encoder for m in (model.prop_mlp_0, model.nerf_mlp)]
     table_ids = {id(e.embeddings) for e in encoders}
     dense = [p for p in model.parameters() if id(p) not in table_ids]
+    skynet = None
+    if sky:     # scripts/train_waymo.sh: model_sky = True (models.py:L84-92, L326-337): + 120 samples x 8x256 MLP per ray
+        from ucnerf_b200 import synthetic
+        skynet = SkyNet(synthetic.synthetic_heads(seed=0)).to(dev)
+        dense += list(skynet.parameters())
+        far = batch["far"].reshape(-1, 1)
+        sky_batch = torch.cat([batch["origins"], batch["directions"], far, torch.full_like(far, float(far[0]) * 1.5),
+                               batch["cam_dirs"]], -1)
     opt = torch.optim.Adam(dense, lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
     grid_opt = GridAdam(encoders, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, hash_decay_mult=0.1, zero_grad=True)
     for e in encoders:                                   # the fused step zeroes these in place every step
@@ -118,6 +171,14 @@ def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", nati
         opt.zero_grad(set_to_none=True)
         renderings, ray_history = level_loop(model, True, batch, 0.5, compute_extras=False, hash_decay='fused', generator=gen,
                                               merge_runs=mr, **kw)
+        if skynet is not None:      # models.py:L336-337, L351-354 (without the brightness affines)
+            if native_mlp == "off":
+                sky_rgb = sky_torch(sky_batch, skynet)["rgb_map"]
+            else:
+                from ucnerf_b200.sky_train import sky_render_rays
+                sky_rgb = sky_render_rays(sky_batch, skynet)["rgb_map"]
+            last = renderings[-1]
+            last["rgb"] = last["rgb"] + (1 - last["weights"].sum(-1, keepdim=True)) * sky_rgb
         loss = compute_loss(batch, renderings, ray_history)
         if timed:
             ph.mark("forward")
@@ -162,7 +223,8 @@ def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", nati
            "warmup": warmup, "ms_per_step": ms / steps, "rays_per_gpu_per_step": n, "samples_per_ray": wl.samples_per_ray,
            "scaling": "weak", "dtype": "f32", "pooled_backward": merge_runs, "data": "synthetic", "phase_ms_per_step": phases,
            "native_launches_per_step": (_lib.launch_count() - launches0) / steps, "final_loss": float(loss.detach()),
-           "gradient_allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
+           "gradient_allreduce_bytes_per_step": grad_bytes if world > 1 else 0, "sky_head": bool(sky),
+           "dense_layers": "cuBLAS fp32 (nn.Linear)" if native_mlp == "off" else "tcgen05 3xTF32 (gemm.tc_linear)",
            "note": "forward / backward through ucnerf_b200.train_forward.level_loop (native resample, cast_rays, pooled "
                    "encode, composite and MLP kernels), torch Adam for the dense layers, fused hash-decay + Adam + zero_grad "
                    "for the tables; N > 1 adds the gradient all-reduce DDP would do"}
@@ -179,6 +241,7 @@ def main():
     ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step (config 5: 65,536 / 8)")
     ap.add_argument("--merge-runs", default="auto", choices=["auto", "off", "interval", "ray"], help="pooled-encode backward variant")
     ap.add_argument("--native-mlp", default="auto", choices=["auto", "on", "off"], help="native MLP kernels vs nn.Linear (cuBLAS)")
+    ap.add_argument("--sky", action="store_true", help="add the sky head (model_sky=True: 120 samples x 8x256 MLP per ray)")
     a = ap.parse_args()
     import torch.distributed as dist
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
@@ -188,7 +251,7 @@ def main():
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    res = run(dev, world, rank, a.steps, a.warmup, a.rays, a.merge_runs, a.native_mlp)
+    res = run(dev, world, rank, a.steps, a.warmup, a.rays, a.merge_runs, a.native_mlp, a.sky)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:

@@ -51,6 +51,8 @@ def parse():
                     + ",".join(sorted(set(EXTRAS_1 + EXTRAS_N))))
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused NVLink tile exchange (default) "
                     "or render + NCCL all-gather")
+    ap.add_argument("--cameras", default="same", choices=["same", "distinct"], help="N > 1: every rank renders the same "
+                    "camera (identical work per rank, default) or rank r renders camera r")
     ap.add_argument("--chunk-rays", type=int, default=0)
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -379,7 +381,11 @@ def run_ours(args):
     for kv in args.option:
         k, v = kv.split("=")
         r.set_option(k, int(v))
-    rays_h = synthetic.pinhole_rays(wl.height, wl.width, seed=rank)   # every rank renders its own camera
+    # every rank renders one frame of the workload: the SAME camera by default, so that the work per rank is identical and
+    # the N-GPU number measures the system (exchange, clocks, launch path), not the scene variance between camera poses
+    # (--cameras distinct: rank r renders camera r; frames then differ by a few per cent and max-over-ranks pays for it)
+    cam_seed = rank if args.cameras == "distinct" else 0
+    rays_h = synthetic.pinhole_rays(wl.height, wl.width, seed=cam_seed)
     n = rays_h["origins"].shape[0]
     rays_d = {k: v.to(dev) for k, v in rays_h.items()}
     # weak scaling = one image of world * n rays, rank `rank` owns tile [start, stop) (render.shard_bounds), the tiles
@@ -467,7 +473,7 @@ def run_ours(args):
     line_extra = {}
     # ---- end-to-end from camera parameters: rays generated on the GPU (ucnerf_render_camera_host) -----------
     if "e2e_camera" in extras:
-        cam = synthetic.pinhole_camera(wl.height, wl.width, seed=rank)
+        cam = synthetic.pinhole_camera(wl.height, wl.width, seed=cam_seed)
         with Clocks(rank, local) as ck:
             ms_cam = timed(cx, lambda: r.render_camera(*cam, want=("packed",), host_out=out_h), args.steps, 2)
         line_extra["e2e_camera"] = {
@@ -560,6 +566,7 @@ def run_ours(args):
                        "samples_per_ray": spr, "prop_samples": wl.num_prop_samples, "nerf_samples": wl.num_nerf_samples,
                        "grid_levels": [wl.grid_levels(d) for d in wl.prop_desired] + [wl.grid_levels(wl.nerf_desired)],
                        "log2_hashmap_size": wl.log2_hashmap_size, "parallelism": f"ray-tile x{world}, replicated model",
+                       "cameras": args.cameras,
                        "collective": ("none" if world == 1 else
                                       "fused: compositing kernel stores the packed tiles into every rank's image over NVLink "
                                       "peer memory (peer.PeerImage) + one 4-byte all_reduce per step" if peer is not None else

@@ -305,12 +305,22 @@ composite_kernel(const CompositeParams p) {
             o[1] = make_float4(ro.acc, ro.dist_mean, ro.dist_median, ro.dist_p5);
             o[2] = make_float4(ro.dist_p95, ro.depth_raw, 0.f, 0.f);
         }
-        // fused tile exchange: the finished row goes to every rank's image (posted stores over NVLink for the peers)
-        for (int k = 0; k < p.n_peers; ++k) {
-            float4* o = reinterpret_cast<float4*>(p.peer_packed[k] + 12 * ((size_t)p.peer_row0 + ray));
-            o[0] = make_float4(ro.rgb[0], ro.rgb[1], ro.rgb[2], ro.depth);
-            o[1] = make_float4(ro.acc, ro.dist_mean, ro.dist_median, ro.dist_p5);
-            o[2] = make_float4(ro.dist_p95, ro.depth_raw, 0.f, 0.f);
+    }
+    // fused tile exchange: the finished row goes to every rank's image - lane k stores it to image k (this rank's own with a
+    // local store, the peers' with posted stores over NVLink), so the n_peers x 48 bytes leave in one store instruction
+    // per float4 instead of serially from one lane
+    if (p.n_peers > 0) {
+        float4 a = make_float4(ro.rgb[0], ro.rgb[1], ro.rgb[2], ro.depth);
+        float4 b = make_float4(ro.acc, ro.dist_mean, ro.dist_median, ro.dist_p5);
+        float4 c = make_float4(ro.dist_p95, ro.depth_raw, 0.f, 0.f);
+        a.x = __shfl_sync(0xffffffffu, a.x, 0); a.y = __shfl_sync(0xffffffffu, a.y, 0); a.z = __shfl_sync(0xffffffffu, a.z, 0);
+        a.w = __shfl_sync(0xffffffffu, a.w, 0);
+        b.x = __shfl_sync(0xffffffffu, b.x, 0); b.y = __shfl_sync(0xffffffffu, b.y, 0); b.z = __shfl_sync(0xffffffffu, b.z, 0);
+        b.w = __shfl_sync(0xffffffffu, b.w, 0);
+        c.x = __shfl_sync(0xffffffffu, c.x, 0); c.y = __shfl_sync(0xffffffffu, c.y, 0);
+        if (ex.lane < p.n_peers) {
+            float4* o = reinterpret_cast<float4*>(p.peer_packed[ex.lane] + 12 * ((size_t)p.peer_row0 + ray));
+            o[0] = a; o[1] = b; o[2] = c;
         }
     }
 }

@@ -36,7 +36,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 EXTRAS_1 = ("parity", "e2e_camera", "e2e_render_image", "target_1024spp", "with_heads", "train_step", "gpu_reference",
-            "cpu_baseline")
+            "cpu_baseline")          # (the default N = 1 run takes about 40 s)
 EXTRAS_N = ("strong_scaling_full_res", "train_step")
 
 
@@ -676,9 +676,15 @@ def full_res_with_heads(cx, r, synthetic, R, local):
 
 def train_step(cx, local):
     """BASELINE.json configs[4]: one optimisation step (forward + backward + exchange + step), 8,192 rays per GPU, through
-    bench_train.py's recipe."""
+    bench_train.py's recipe; `with_sky_head` = the same step with `Config.model_sky` (scripts/train_waymo.sh)."""
     import bench_train as BT
-    res = BT.run(cx.dev, cx.world, cx.rank, steps=8, warmup=3, rays=8192)
+    with Clocks(cx.rank, local) as ck:
+        res = BT.run(cx.dev, cx.world, cx.rank, steps=8, warmup=3, rays=8192)
+    res["clocks"] = ck.result
+    with Clocks(cx.rank, local) as ck:
+        sky = BT.run(cx.dev, cx.world, cx.rank, steps=4, warmup=2, rays=8192, sky=True)
+    res["with_sky_head"] = {k: sky[k] for k in ("value", "ms_per_step", "phase_ms_per_step", "gradient_allreduce_bytes_per_step")}
+    res["with_sky_head"]["clocks"] = ck.result
     return res
 
 

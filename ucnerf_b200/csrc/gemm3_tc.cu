@@ -44,7 +44,10 @@ constexpr uint32_t kStageBytes = 2 * kATile + 2 * kBTile;  // 96 KB: A hi | A lo
 constexpr int kStages = 2;
 constexpr uint32_t kSmemMisc = kStages * kStageBytes;      // 196608
 constexpr uint32_t kOffBar = 0, kOffTmem = 128, kOffBias = 256;
-constexpr uint32_t kSmemTotal = kSmemMisc + kOffBias + 1024 + 1024;   // + bias[256] + manual 1 KB alignment slack
+constexpr uint32_t kOffStage = kOffBias + 1024;                       // epilogue staging: 4 warps x 32 rows x 144 B
+constexpr uint32_t kEpiRowBytes = 144, kEpiWarpBytes = 32 * kEpiRowBytes;
+constexpr uint32_t kSmemTotal = kSmemMisc + kOffStage + 4 * kEpiWarpBytes + 1024;   // + manual 1 KB alignment slack
+static_assert(kSmemTotal <= 232448, "shared memory budget");
 constexpr int kLoaderThreads = 256, kEpiWarp0 = 8, kMmaWarp = 12, kCopyWarp = 13, kThreads = 14 * 32;
 constexpr uint32_t kBlobChunk = 2 * kBTile;                // packed weights: hi tile | lo tile per K chunk (64 KB)
 constexpr int kMaxChunks = 24;
@@ -318,28 +321,46 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_nt_kernel(const __grid_cons
 
     if (warp < 8) {
         // ================= loaders =================
+        // Software pipeline over the flattened (tile, chunk) sequence: the global loads of step i + 1 are issued before the
+        // split / store of step i, and neither needs the stage to be free - the loads are in flight while the MMAs of
+        // earlier chunks still read it.
         const int t = threadIdx.x;
-        uint32_t k = 0;   // stage uses so far
-        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+        const uint32_t nsteps = my_tiles * p.nchunks;
+        auto fetch = [&](float4 (&x)[4], uint32_t i) {
+            const uint32_t tile = blockIdx.x + (i / p.nchunks) * gridDim.x, c = i % p.nchunks;
+            const Chunk& ch = p.ch[c];
             const uint32_t row0 = tile * 128, rows_valid = min(128u, p.M - row0);
-            for (uint32_t c = 0; c < p.nchunks; ++c, ++k) {
-                const Chunk& ch = p.ch[c];
-                const int s = k & 1;
-                // the global loads do not need the stage: they are in flight while the MMAs of chunk k - 2 still read it
-                float4 xa[4];
-                fetch_rowmajor<4>(xa, ch.a + (size_t)row0 * ch.lda, ch.lda, 128, rows_valid, ch.kvalid, ch.veca != 0, t);
-                if (!mbar_wait(sh.bar(EMPTY0 + s), ((k >> 1) & 1) ^ 1, p.dbg, 1, EMPTY0 + s, tile, c)) goto done;
-                uint8_t* st = sh.stage(s);
-                store_kmajor<4>(xa, st, kATile, 128, t);
-                if (!p.bblob) load_rowmajor_tile<8>(st + 2 * kATile, kBTile, ch.b, ch.ldb, p.npad, p.N, ch.kvalid, ch.vecb != 0, t);
-                fence_proxy_async();
-                mbar_arrive(sh.bar(FULL0 + s));
+            fetch_rowmajor<4>(x, ch.a + (size_t)row0 * ch.lda, ch.lda, 128, rows_valid, ch.kvalid, ch.veca != 0, t);
+        };
+        auto commit = [&](const float4 (&x)[4], uint32_t i) -> bool {
+            const int s = i & 1;
+            if (!mbar_wait(sh.bar(EMPTY0 + s), ((i >> 1) & 1) ^ 1, p.dbg, 1, EMPTY0 + s, i, 0)) return false;
+            uint8_t* st = sh.stage(s);
+            store_kmajor<4>(x, st, kATile, 128, t);
+            if (!p.bblob) {
+                const Chunk& ch = p.ch[i % p.nchunks];
+                load_rowmajor_tile<8>(st + 2 * kATile, kBTile, ch.b, ch.ldb, p.npad, p.N, ch.kvalid, ch.vecb != 0, t);
+            }
+            fence_proxy_async();
+            mbar_arrive(sh.bar(FULL0 + s));
+            return true;
+        };
+        float4 x0[4], x1[4];
+        if (nsteps > 0) fetch(x0, 0);
+        for (uint32_t i = 0; i < nsteps; i += 2) {
+            if (i + 1 < nsteps) fetch(x1, i + 1);
+            if (!commit(x0, i)) goto done;
+            if (i + 1 < nsteps) {
+                if (i + 2 < nsteps) fetch(x0, i + 2);
+                if (!commit(x1, i + 1)) goto done;
             }
         }
     } else if (warp < kMmaWarp) {
         // ================= epilogue: thread e <-> row e of the tile =================
         const int e = threadIdx.x - 32 * kEpiWarp0;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        uint8_t* stage_w = sh.smem + kSmemMisc + kOffStage + (warp & 3) * kEpiWarpBytes;
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -357,15 +378,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_nt_kernel(const __grid_cons
                         v[i] = __uint_as_float(r[i]) + sBias[(32 * j + i) & 255];
                         if (p.relu) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (p.cvec && 32 * j + 32 <= p.N) {   // 128 contiguous bytes of this thread's row
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            reinterpret_cast<float4*>(crow + 32 * j)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    } else {
+                    if (!(p.cvec && 32 * j + 32 <= p.N)) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (32 * j + i < p.N) crow[32 * j + i] = v[i];
+                    } else {
+                        // thread = row would store 32 different 128-byte lines per instruction: stage the warp's 32 x 32 block
+                        // in shared memory and write it out 4 full rows (4 x 128 B) per instruction instead
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(stage_w + lane * kEpiRowBytes + 16 * q) =
+                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                     }
+                }
+                if (p.cvec && 32 * j + 32 <= p.N) {      // (warp-uniform)
+                    __syncwarp();
+                    const uint32_t wrow0 = tile * 128 + (uint32_t)(warp & 3) * 32;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t rr = 4 * i + (lane >> 3), pc = lane & 7;
+                        const float4 x = *reinterpret_cast<const float4*>(stage_w + rr * kEpiRowBytes + 16 * pc);
+                        if (wrow0 + rr < p.M) *reinterpret_cast<float4*>(p.C + (size_t)(wrow0 + rr) * p.ldc + 32 * j + 4 * pc) = x;
+                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -424,24 +459,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_tn_kernel(const __grid_cons
 
     if (warp < 8) {
         uint32_t k = 0;
-        for (uint32_t c = c_begin; c < c_end; ++c, ++k) {
-            const int s = k & 1;
-            uint8_t* st = sh.stage(s);
-            if (p.mn_major) {
-                // the global loads do not need the stage: they are in flight while the MMAs of chunk k - 2 still read it
+        if (p.mn_major) {
+            // the global loads do not need the stage: they are in flight while the MMAs of chunk k - 2 still read it.
+            // (Issuing the loads of chunk c + 1 before the stores of chunk c as well - 24 float4 in flight per thread - was
+            // measured 2.8x SLOWER: 128 registers + 184 bytes of spills in the loader warps.)
+            const int t = threadIdx.x;
+            for (uint32_t c = c_begin; c < c_end; ++c, ++k) {
+                const int s = k & 1;
                 float4 xa[4], xb[8];
-                fetch_mnmajor<4>(xa, p.A, p.lda, 128, n1_0, p.N1, c * 32, p.M, p.veca != 0, threadIdx.x);
-                fetch_mnmajor<8>(xb, p.B, p.ldb, npad2, n2_0, p.N2, c * 32, p.M, p.vecb != 0, threadIdx.x);
+                fetch_mnmajor<4>(xa, p.A, p.lda, 128, n1_0, p.N1, c * 32, p.M, p.veca != 0, t);
+                fetch_mnmajor<8>(xb, p.B, p.ldb, npad2, n2_0, p.N2, c * 32, p.M, p.vecb != 0, t);
                 if (!mbar_wait(sh.bar(EMPTY0 + s), ((k >> 1) & 1) ^ 1, p.dbg, 11, EMPTY0 + s, c, 0)) goto done;
-                store_mnmajor<4>(xa, st, kATile, 128, threadIdx.x);
-                store_mnmajor<8>(xb, st + 2 * kATile, kBTile, npad2, threadIdx.x);
-            } else {
+                uint8_t* st = sh.stage(s);
+                store_mnmajor<4>(xa, st, kATile, 128, t);
+                store_mnmajor<8>(xb, st + 2 * kATile, kBTile, npad2, t);
+                fence_proxy_async();
+                mbar_arrive(sh.bar(FULL0 + s));
+            }
+        } else {   // transposing loader + K-major tiles (the first version; env UCNERF_GEMM_TN_TRANSPOSE=1)
+            for (uint32_t c = c_begin; c < c_end; ++c, ++k) {
+                const int s = k & 1;
+                uint8_t* st = sh.stage(s);
                 if (!mbar_wait(sh.bar(EMPTY0 + s), ((k >> 1) & 1) ^ 1, p.dbg, 11, EMPTY0 + s, c, 0)) goto done;
                 load_transposed_tile<16>(st, kATile, p.A, p.lda, 128, n1_0, p.N1, c * 32, p.M, warp, lane);
                 load_transposed_tile<16>(st + 2 * kATile, kBTile, p.B, p.ldb, npad2, n2_0, p.N2, c * 32, p.M, warp, lane);
+                fence_proxy_async();
+                mbar_arrive(sh.bar(FULL0 + s));
             }
-            fence_proxy_async();
-            mbar_arrive(sh.bar(FULL0 + s));
         }
     } else if (warp < kMmaWarp) {
         const int e = threadIdx.x - 32 * kEpiWarp0;

@@ -452,10 +452,11 @@ def run_ours(args):
         dev_in = {k: torch.empty_like(v, device=dev) for k, v in pin2.items()}
 
         def e2e_step():     # host rays in -> device render + tile exchange -> this rank's rows of the image back
-            for k in dev_in:
-                dev_in[k].copy_(pin2[k], non_blocking=True)
-            if peer is not None:
-                img, _ = peer.render(r, dev_in, 1.0, dev_in["rand_vec"], start)
+            if peer is None:
+                for k in dev_in:
+                    dev_in[k].copy_(pin2[k], non_blocking=True)
+            if peer is not None:      # H2D of chunk c + 1 under chunk c's kernels, tiles written to every rank's image
+                img = peer.render_host(r, pin, 1.0, start)
             else:
                 o = r.render_rays(dev_in, 1.0, dev_in["rand_vec"], ("packed",))
                 img = R.gather_tiles(o["packed"], world, world * n)

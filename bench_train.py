@@ -141,7 +141,7 @@ def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", nati
     import torch.distributed as dist
     from ucnerf_b200 import _lib
     from ucnerf_b200.gridencoder.optim import GridAdam
-    from ucnerf_b200.parallel_train import allreduce_gradients
+    from ucnerf_b200.parallel_train import OverlappedGradientExchange
     from ucnerf_b200.train_forward import level_loop
     model, wl = build_model(dev)
     batch, n = make_batch(rays, seed=rank, dev=dev)
@@ -161,6 +161,7 @@ def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", nati
     for e in encoders:                                   # the fused step zeroes these in place every step
         e.embeddings.grad = torch.zeros_like(e.embeddings)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    exchange = OverlappedGradientExchange(dense, [e.embeddings for e in encoders])     # table all-reduces start inside backward
     ph = Phases()
     mr = {"auto": "auto", "off": False, "interval": True, "ray": "ray"}[merge_runs]
     kw = {} if native_mlp == "auto" else {"native_mlp": native_mlp == "on"}
@@ -186,7 +187,7 @@ def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", nati
         if timed:
             ph.mark("backward")
         if world > 1:
-            allreduce_gradients(dense, [e.embeddings for e in encoders])
+            exchange.finish()
             if timed:
                 ph.mark("exchange")
         opt.step()
@@ -225,9 +226,11 @@ def run(dev, world, rank, steps=10, warmup=3, rays=8192, merge_runs="auto", nati
            "native_launches_per_step": (_lib.launch_count() - launches0) / steps, "final_loss": float(loss.detach()),
            "gradient_allreduce_bytes_per_step": grad_bytes if world > 1 else 0, "sky_head": bool(sky),
            "dense_layers": "cuBLAS fp32 (nn.Linear)" if native_mlp == "off" else "tcgen05 3xTF32 (gemm.tc_linear)",
+           "exchange": "table all-reduces (NCCL AVG) start from post-accumulate-grad hooks during backward; `exchange` = what is left",
            "note": "forward / backward through ucnerf_b200.train_forward.level_loop (native resample, cast_rays, pooled "
                    "encode, composite and MLP kernels), torch Adam for the dense layers, fused hash-decay + Adam + zero_grad "
                    "for the tables; N > 1 adds the gradient all-reduce DDP would do"}
+    exchange.close()
     del model, opt, grid_opt
     torch.cuda.empty_cache()
     return res

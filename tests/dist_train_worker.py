@@ -37,6 +37,20 @@ def main():
         assert torch.allclose(p.grad, b * k, atol=1e-6)
     expect = 4 * (sum(b.numel() for b in base_d) + sum(b.numel() for b in base_t))
     assert sent == expect, (sent, expect)
+    # the overlapped variant: table all-reduces start from post-accumulate-grad hooks inside backward()
+    from ucnerf_b200.parallel_train import OverlappedGradientExchange
+    t2 = [torch.nn.Parameter(torch.ones((50, 4))), torch.nn.Parameter(torch.ones((7, 4)))]
+    d2 = [torch.nn.Parameter(torch.ones(5)), torch.nn.Parameter(torch.ones((2, 3)))]
+    ex = OverlappedGradientExchange(d2, t2)
+    for step in range(2):
+        for p in t2 + d2:
+            p.grad = None
+        loss = (rank + 1.0) * (t2[0].sum() * 2 + (t2[1] ** 2).sum() + d2[0].sum() * 3 + d2[1].sum())
+        loss.backward()
+        ex.finish()
+        assert torch.allclose(t2[0].grad, torch.full((50, 4), 2 * k)) and torch.allclose(t2[1].grad, torch.full((7, 4), 2 * k))
+        assert torch.allclose(d2[0].grad, torch.full((5,), 3 * k)) and torch.allclose(d2[1].grad, torch.full((2, 3), k))
+    ex.close()
     dist.barrier()
     if rank == 0:
         print(f"TRAIN_EXCHANGE_OK gloo {world}")

@@ -274,7 +274,8 @@ struct Shared {
     __device__ uint8_t* stage(int s) const { return smem + (size_t)s * kStageBytes; }
 };
 
-__device__ __forceinline__ Shared setup(uint8_t* smem_raw, int warp, uint32_t& tmem_base, uint32_t full_count = kLoaderThreads) {
+__device__ __forceinline__ Shared setup(uint8_t* smem_raw, int warp, uint32_t& tmem_base, uint32_t full_count = kLoaderThreads,
+                                        int mma_warp = kMmaWarp) {
     Shared sh;
     sh.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* misc = sh.smem + kSmemMisc;
@@ -286,7 +287,7 @@ __device__ __forceinline__ Shared setup(uint8_t* smem_raw, int warp, uint32_t& t
         mbar_init(sh.bar(ACC_EMPTY0), 128); mbar_init(sh.bar(ACC_EMPTY1), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kMmaWarp) {   // whole warp: allocate all 512 TMEM columns
+    if (warp == mma_warp) {   // whole warp: allocate all 512 TMEM columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(misc + kOffTmem)), "r"(512)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -298,10 +299,10 @@ __device__ __forceinline__ Shared setup(uint8_t* smem_raw, int warp, uint32_t& t
     return sh;
 }
 
-__device__ __forceinline__ void teardown(int warp, uint32_t tmem_base) {
+__device__ __forceinline__ void teardown(int warp, uint32_t tmem_base, int mma_warp = kMmaWarp) {
     tc_fence_before();
     __syncthreads();
-    if (warp == kMmaWarp) {
+    if (warp == mma_warp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libucnerf_b200.so")
 OBJ = os.path.join(HERE, "csrc", "build")
-SOURCES = ["grid_encode.cu", "grid_adam.cu", "pooled_encode.cu", "resample_op.cu", "composite_train.cu", "cast_rays_op.cu", "ray_gen.cu", "peer.cu", "gemm3_tc.cu", "ray_march.cu", "sample_encode.cu", "color_mlp_tc.cu", "sky_mlp_tc.cu", "sky_model.cu", "model.cu"]
+SOURCES = ["grid_encode.cu", "grid_adam.cu", "pooled_encode.cu", "resample_op.cu", "composite_train.cu", "cast_rays_op.cu", "ray_gen.cu", "peer.cu", "gemm3_tc.cu", "ray_march.cu", "sample_encode.cu", "color_mlp_tc.cu", "sky_mlp_tc.cu", "sky_mlp_tc2.cu", "sky_model.cu", "model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "128"]
 

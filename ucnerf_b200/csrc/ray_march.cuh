@@ -100,6 +100,10 @@ struct SkyTcParams {
     float* raw;               // [n_rows][4] = rgb_raw, alpha_raw
     uint32_t* dbg;
     uint32_t debug_flags;     // bit 2: in-kernel wait profiler (env UCNERF_SKY_DEBUG, development only)
+    // second pipeline (sky_mlp_tc2.cu): 60 weight half-chunks (128 output columns x 64 K, hi | lo FP16, 32 KB stride) and
+    // the two K = 3 blocks for the CUDA cores: [256] float4 = act scale x (W0[c][0..2], b0[c]) / (W5[c][0..2], 0)
+    const uint8_t* wblob2;
+    const float *w0x, *w5x;
 };
 
 struct CompositeParams {
@@ -140,6 +144,10 @@ int launch_sky_mlp_tc(const SkyTcParams& p, cudaStream_t st);
 int launch_sky_view_bias(const float* views, const float* wv_view, const float* bv, float* out, uint32_t n_rays, cudaStream_t st);
 int launch_sky_composite(const float* raw, const float* directions, const float* far, const float* t_vals, float sky_far,
                          int n_samples, float* out, uint32_t n_rays, cudaStream_t st);
+int launch_sky_mlp_tc2(const SkyTcParams& p, uint32_t* dbg, cudaStream_t st);
+uint32_t sky_tc2_blob_bytes();
+int sky_tc2_half_steps();
+uint32_t* sky_tc_dbg_buffer();
 int sky_tc_status(uint32_t* out32);
 uint32_t sky_tc_blob_bytes();
 int sky_tc_steps();

@@ -441,12 +441,17 @@ int sky_tc_status(uint32_t* out32) {
     return 0;
 }
 
+uint32_t* sky_tc_dbg_buffer() {
+    if (!g_sky_dbg) {
+        if (cudaMalloc(&g_sky_dbg, 32 * sizeof(uint32_t)) != cudaSuccess) return nullptr;
+        cudaMemset(g_sky_dbg, 0, 32 * sizeof(uint32_t));
+    }
+    return g_sky_dbg;
+}
+
 int launch_sky_mlp_tc(const SkyTcParams& p_in, cudaStream_t st) {
     if (p_in.n_rows == 0) return 0;
-    if (!g_sky_dbg) {
-        UC_CUDA_OK(cudaMalloc(&g_sky_dbg, 32 * sizeof(uint32_t)));
-        UC_CUDA_OK(cudaMemset(g_sky_dbg, 0, 32 * sizeof(uint32_t)));
-    }
+    UC_REQUIRE(sky_tc_dbg_buffer() != nullptr, "sky: cannot allocate the watchdog record");
     SkyTcParams p = p_in;
     p.dbg = g_sky_dbg;
     if (const char* e = getenv("UCNERF_SKY_DEBUG")) p.debug_flags = (uint32_t)atoi(e);   // profiling experiments only

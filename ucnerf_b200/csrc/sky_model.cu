@@ -3,6 +3,7 @@
 // ucnerf_sky_* (include/ucnerf_b200.h).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -55,7 +56,9 @@ using namespace ucnerf;
 
 struct ucnerf_sky {
     int n_samples = 120;
-    SkyBuf wblob, bias8, w_alpha, rgb_w, wv_view, bv, t_vals, view_bias, raw;
+    SkyBuf wblob, wblob2, w0x, w5x, bias8, w_alpha, rgb_w, wv_view, bv, t_vals, view_bias, raw;
+    int pipeline = 1;   // 1: sky_mlp_tc.cu (default), 2: half-pass pipeline (sky_mlp_tc2.cu: measured 5 % slower, kept as an
+                        // experiment; env UCNERF_SKY_PIPELINE=2)
     float k[10];
     float b_alpha = 0.f, rgb_b[3] = {0, 0, 0};
     int64_t chunk_rays = 262144;
@@ -64,7 +67,7 @@ struct ucnerf_sky {
 
 extern "C" int ucnerf_sky_destroy(ucnerf_sky* s) {
     if (!s) return 0;
-    for (SkyBuf* b : {&s->wblob, &s->bias8, &s->w_alpha, &s->rgb_w, &s->wv_view, &s->bv, &s->t_vals, &s->view_bias, &s->raw})
+    for (SkyBuf* b : {&s->wblob, &s->wblob2, &s->w0x, &s->w5x, &s->bias8, &s->w_alpha, &s->rgb_w, &s->wv_view, &s->bv, &s->t_vals, &s->view_bias, &s->raw})
         b->release();
     delete s;
     return 0;
@@ -135,6 +138,35 @@ extern "C" int ucnerf_sky_create(const ucnerf_sky_desc* d, ucnerf_sky** out) {
         for (int j = 0; j < 4; ++j) pack_block(W[l], 256, 64 * j, 64, 256, sw[l]);  // steps 22..29
     for (int j = 0; j < 4; ++j) pack_block(wfold, 256, 64 * j, 64, 128, sw[8]);     // steps 30..33: folded view layer (N = 128)
     if (step != nsteps) { set_error("sky_create: internal chunk count"); return fail(1); }
+    // ---- second pipeline: 60 half-chunks (128 output columns x 64 K) in the order its MMA thread consumes them:
+    //      layers 1..7: pass h (columns 128 h ..) x K chunk j; then the folded view layer (N = 128) ----
+    std::vector<uint8_t> blob2(sky_tc2_blob_bytes(), 0);
+    {
+        const size_t stride2 = blob2.size() / sky_tc2_half_steps();
+        std::vector<float> wt2((size_t)64 * 128);
+        int hs = 0;
+        auto pack_half = [&](const std::vector<float>& w, int fin, int col0, int n0, float scale) {
+            for (int k = 0; k < 64; ++k)
+                for (int n = 0; n < 128; ++n) wt2[(size_t)k * 128 + n] = w[(size_t)(n0 + n) * fin + col0 + k];
+            sky_tc_pack_chunk(wt2.data(), 128, scale, blob2.data() + stride2 * hs);
+            ++hs;
+        };
+        for (int l = 1; l <= 7; ++l)
+            for (int h = 0; h < 2; ++h)
+                for (int j = 0; j < 4; ++j) pack_half(W[l], l == 5 ? 259 : 256, (l == 5 ? 3 : 0) + 64 * j, 128 * h, sw[l]);
+        for (int j = 0; j < 4; ++j) pack_half(wfold, 256, 64 * j, 0, sw[8]);
+        if (hs != sky_tc2_half_steps()) { set_error("sky_create: internal half-chunk count"); return fail(1); }
+    }
+    std::vector<float> w0x((size_t)256 * 4), w5x((size_t)256 * 4);
+    for (int c = 0; c < 256; ++c) {
+        for (int i = 0; i < 3; ++i) {
+            w0x[(size_t)4 * c + i] = act * W[0][(size_t)c * 3 + i];
+            w5x[(size_t)4 * c + i] = act * W[5][(size_t)c * 259 + i];
+        }
+        w0x[(size_t)4 * c + 3] = act * B[0][c];
+        w5x[(size_t)4 * c + 3] = 0.f;
+    }
+    if (const char* e = getenv("UCNERF_SKY_PIPELINE")) s->pipeline = atoi(e) == 2 ? 2 : 1;
     for (int l = 0; l < 8; ++l) s->k[l] = 1.f / sw[l];
     s->k[8] = 1.f / (act * sw[8]);
     s->k[9] = 0.f;
@@ -156,6 +188,9 @@ extern "C" int ucnerf_sky_create(const ucnerf_sky_desc* d, ucnerf_sky** out) {
         for (int i = 0; i < steps; ++i) tv[i] = i < steps / 2 ? std::fmaf(st, (float)i, 0.f) : std::fmaf(-st, (float)(steps - i - 1), 1.f);
     }
     if (int e = sky_upload(s->wblob, blob.data(), blob.size())) return fail(e);
+    if (int e = sky_upload(s->wblob2, blob2.data(), blob2.size())) return fail(e);
+    if (int e = sky_upload(s->w0x, w0x.data(), w0x.size() * 4)) return fail(e);
+    if (int e = sky_upload(s->w5x, w5x.data(), w5x.size() * 4)) return fail(e);
     if (int e = sky_upload(s->bias8, bias8.data(), bias8.size() * 4)) return fail(e);
     if (int e = sky_upload(s->w_alpha, Wa.data(), 256 * 4)) return fail(e);
     if (int e = sky_upload(s->rgb_w, rgbw.data(), rgbw.size() * 4)) return fail(e);
@@ -187,7 +222,12 @@ extern "C" int ucnerf_sky_render(ucnerf_sky* s, uint64_t n_rays, const float* or
         p.w_alpha = s->w_alpha.as<float>(); p.b_alpha = s->b_alpha; p.rgb_w = s->rgb_w.as<float>();
         std::memcpy(p.rgb_b, s->rgb_b, sizeof(p.rgb_b));
         p.raw = s->raw.as<float>();
-        if (int e = launch_sky_mlp_tc(p, st)) return e;
+        p.wblob2 = s->wblob2.as<uint8_t>(); p.w0x = s->w0x.as<float>(); p.w5x = s->w5x.as<float>();
+        if (s->pipeline == 2) {
+            uint32_t* dbg = sky_tc_dbg_buffer();
+            UC_REQUIRE(dbg != nullptr, "sky: cannot allocate the watchdog record");
+            if (int e = launch_sky_mlp_tc2(p, dbg, st)) return e;
+        } else if (int e = launch_sky_mlp_tc(p, st)) return e;
         if (int e = launch_sky_composite(s->raw.as<float>(), directions + 3 * r0, far + r0, s->t_vals.as<float>(), (float)sky_far,
                                          s->n_samples, sky_rgb + 3 * r0, n, st)) return e;
     }

@@ -87,6 +87,7 @@ struct ucnerf_model {
     uint64_t peer_row0 = 0;
     int encode_runs = 0;  // cell-run reuse in sample_encode_kernel (bit 0 = proposal levels, bit 1 = NeRF level): measured
                           // slower on B200 (profiles/r1_summary.md), kept as an option
+    int encode_mlp_mma = 3;  // density layer of sample_encode_kernel on mma.sync 3xTF32 (bit 0 = proposal levels, bit 1 = NeRF level)
     int warp_rays_log2[2] = {5, 5};  // sample_encode_kernel warp shape {proposal levels, NeRF level}: 2^k rays x 2^(5-k) samples
     bool timing = false;
     float ms[5] = {0, 0, 0, 0, 0};
@@ -365,6 +366,7 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         sp.density = (nerf && o.sample_density) ? o.sample_density + ray0 * S : m->density.as<float>();
         std::memcpy(sp.g2, ls.g2, sizeof(sp.g2));
         sp.cell_runs = (m->encode_runs >> (nerf ? 1 : 0)) & 1;
+        sp.mlp_mma = (m->encode_mlp_mma >> (nerf ? 1 : 0)) & 1;
         sp.rw_log2 = m->warp_rays_log2[nerf ? 1 : 0];
         if (S % (32 >> sp.rw_log2) != 0) sp.rw_log2 = 5;   // sample blocks must tile S
         float* rgb_s = nullptr;
@@ -490,6 +492,7 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
     if (k == "chunk_rays") { UC_REQUIRE(value >= 1, "chunk_rays must be >= 1"); m->chunk_rays = value; }
     else if (k == "color_mlp") { UC_REQUIRE(value >= 0 && value <= 2, "color_mlp: 0 = fp32 SIMT, 1 = tensor core, 2 = auto"); m->color_mode = (int)value; }
     else if (k == "encode_runs") { UC_REQUIRE(value >= 0 && value <= 3, "encode_runs: bit 0 = proposal levels, bit 1 = NeRF level"); m->encode_runs = (int)value; }
+    else if (k == "encode_mlp_mma") { UC_REQUIRE(value >= 0 && value <= 3, "encode_mlp_mma: bit 0 = proposal levels, bit 1 = NeRF level"); m->encode_mlp_mma = (int)value; }
     else if (k == "warp_rays_prop" || k == "warp_rays_nerf") {
         UC_REQUIRE(value == 32 || value == 16 || value == 8 || value == 4, "warp_rays_*: 32, 16, 8 or 4 rays per warp");
         m->warp_rays_log2[k == "warp_rays_nerf" ? 1 : 0] = value == 32 ? 5 : value == 16 ? 4 : value == 8 ? 3 : 2;

@@ -47,6 +47,7 @@ struct SampleParams {
     float g2[16];            // float(grid_sizes[l]^2)
     int rw_log2;             // warp shape of sample_encode_kernel: 2^rw_log2 rays x 2^(5 - rw_log2) samples (5 = 32 rays x 1)
     int cell_runs;           // 1: level-outer loop with cell-run reuse of the gathered corners (sample_encode.cu)
+    int mlp_mma;             // 1: density layer on the tensor cores (mma.sync 3xTF32), 0: FFMA2 forms (sample_encode.cu)
 };
 
 // Colour MLP with the linear bottleneck layer folded into its two consumers (exact algebra, see model.cu):
@@ -154,7 +155,10 @@ int sky_tc_steps();
 float sky_tc_act_scale();
 void sky_tc_pack_chunk(const float* wt_rows, int n_cols, float scale, uint8_t* dst);
 int sample_encode_lmax(int L);
-// h1 column c holds hidden unit kH1Perm(c) of density_layer.0 (layout written by sample_encode_kernel)
-inline int h1_perm(int c) { return (c / 16) + 4 * (c % 16); }  // padded level count used by the kernel instantiation (0 = unsupported)
+// h1 column c holds hidden unit h1_perm(c) of density_layer.0 (layout written by sample_encode_kernel): lane t of a
+// quad owns the accumulator columns {8 nt + 2 t + e} of the mma.sync C fragments, stored as 16 consecutive floats
+// -> column 16 t + 2 nt + e.  h1_col is the inverse.
+__host__ __device__ inline int h1_perm(int c) { return 8 * ((c % 16) / 2) + 2 * (c / 16) + (c % 2); }
+__host__ __device__ inline int h1_col(int u) { return 16 * ((u % 8) / 2) + 2 * (u / 8) + (u % 2); }
 
 }  // namespace ucnerf

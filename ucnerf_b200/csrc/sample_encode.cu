@@ -21,6 +21,9 @@ constexpr int kSampleThreads = 128;
 #ifndef UC_MINB_SMALL
 #define UC_MINB_SMALL 5   // LMAX <= 6  -> 96 registers (6 -> 80 registers spills in the MLP phase)
 #endif
+#ifndef UC_MMA_ONE_PASS_MINB
+#define UC_MMA_ONE_PASS_MINB 4
+#endif
 #ifndef UC_REMAP_PROP
 #define UC_REMAP_PROP 1
 #endif
@@ -43,6 +46,25 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+
+// x rounded to TF32 (10-bit mantissa, round to nearest) as an fp32 value; x - tf32_hi(x) is exact in fp32
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// fp32 -> bf16 (round to nearest even) bit pattern; finite inputs
+__device__ __forceinline__ uint32_t bf16_bits(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return (b + 0x7fffu + ((b >> 16) & 1u)) >> 16;
+}
+// D += A B, m16n8k8, A row-major [16][8], B column-major [8][8] (legacy warp-level tensor-core path: at 64 outputs and
+// K = 24 / 40 per sample the layer is far too small for a tcgen05 tile pipeline to pay its TMEM round trip)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // MODE: 0 dense (index < table size, no reduction), 1 hashed with power-of-two table, 2 generic (runtime flags)
@@ -107,19 +129,30 @@ struct SamplePos {
     int s;
     bool valid;
 };
-__device__ __forceinline__ SamplePos sample_pos(size_t q, uint32_t n_rays, int S, int rw_log2) {
-    const size_t group = q / ((size_t)32 * S);
-    const uint32_t rem = (uint32_t)(q - group * (size_t)32 * S);
-    // rw_log2 = 5: lane -> ray, warp -> sample.  rw_log2 < 5 (experiment, option "warp_rays"): a warp covers 2^rw_log2
-    // rays x 2^(5 - rw_log2) consecutive samples; the warps of a group enumerate (sample block, ray block).
-    const uint32_t lane = rem & 31u, w = rem >> 5, sw_log2 = 5u - (uint32_t)rw_log2;
-    const uint32_t ray_block = w & ((1u << sw_log2) - 1u), sample_block = w >> sw_log2;
-    SamplePos sp;
-    sp.ray = (uint32_t)group * 32u + (ray_block << rw_log2) + (lane & ((1u << rw_log2) - 1u));
-    sp.s = (int)((sample_block << sw_log2) + (lane >> rw_log2));
-    sp.valid = sp.ray < n_rays;
-    return sp;
-}
+// The mapping for the positions q = block0 + i of ONE CTA, with the 64-bit division done once.
+// rw_log2 = 5: lane -> ray, warp -> sample.  rw_log2 < 5 (experiment, option "warp_rays"): a warp covers 2^rw_log2
+// rays x 2^(5 - rw_log2) consecutive samples; the warps of a group enumerate (sample block, ray block).
+struct BlockSamples {
+    uint32_t group, rem0, span, n_rays;
+    int S, rw_log2;
+    __device__ __forceinline__ BlockSamples(size_t block0, uint32_t n_rays_, int S_, int rw_log2_)
+        : span(32u * (uint32_t)S_), n_rays(n_rays_), S(S_), rw_log2(rw_log2_) {
+        const size_t g = block0 / span;
+        group = (uint32_t)g;
+        rem0 = (uint32_t)(block0 - g * span);
+    }
+    __device__ __forceinline__ SamplePos at(uint32_t i) const {
+        uint32_t rem = rem0 + i, grp = group;
+        while (rem >= span) { rem -= span; ++grp; }
+        const uint32_t lane = rem & 31u, w = rem >> 5, sw_log2 = 5u - (uint32_t)rw_log2;
+        const uint32_t ray_block = w & ((1u << sw_log2) - 1u), sample_block = w >> sw_log2;
+        SamplePos sp;
+        sp.ray = grp * 32u + (ray_block << rw_log2) + (lane & ((1u << rw_log2) - 1u));
+        sp.s = (int)((sample_block << sw_log2) + (lane >> rw_log2));
+        sp.valid = sp.ray < n_rays;
+        return sp;
+    }
+};
 
 // ND >= 0: levels [0, ND) are dense, levels >= ND hashed with power-of-two tables (compile-time specialisation);
 // ND < 0: decide per level at run time.
@@ -141,28 +174,66 @@ __device__ __forceinline__ SamplePos sample_pos(size_t q, uint32_t n_rays, int S
 // are bit-identical to the RUNS = false form; only redundant gathers (L1 wavefronts, the limiter) disappear.  The
 // level loop is rolled (per-level constants by dynamic constant-bank index), pooled features go straight to the
 // shared-memory rows the density layer reads.
-template <int LMAX, bool NERF, int ND, int MINB, bool REMAP, bool RUNS>
+//
+// MLP = 2 (default where it pays): the density layer runs on the tensor cores.  A warp multiplies its own 32 feature
+// rows (two m16 tiles) with the 24/40 x 64 weight as mma.sync.m16n8k8 TF32 with the 3-term split (x = hi + lo,
+// lo*hi + hi*lo + hi*hi accumulated in fp32: products exact to about 2^-20, no scaling and no range limit, unlike an
+// FP16 split).  Features never leave the warp: each k-tile (two levels) goes from the registers through a 1.5 KB
+// warp-private transpose buffer into A fragments.  Weights sit in shared memory already split and in fragment order:
+// per (unit, k-tile, t) a float2 {hi[k = t], hi[k = t + 4]} and one word of two bf16 {lo[t], lo[t + 4]} (a bf16 is an
+// exact TF32 operand, and 8 mantissa bits of the 2^-11-sized rest keep the product at 2^-20).  Row strides are padded so
+// that the 64-bit loads of a half warp and the 32-bit loads of a warp are bank-conflict free.  Compared with the FFMA2
+// forms (MLP = 1 / 0, kept as options) the layer's shared-memory wavefronts drop from about 17 to 4 per proposal sample,
+// its 3 K FMAs leave the FP32 pipe, and - measured to matter as much - the CTA needs 16 KB instead of 22 KB of shared
+// memory, which leaves the L1 more room for the gathers (profiles/r2_mma_density.md).
+template <int LMAX>
+struct MmaLayout {
+    static constexpr int KT = LMAX / 2;                                                                // k-tiles of 8 feature columns
+    static constexpr int SH = KT * 8 + (((KT * 8) % 32 == 8 || (KT * 8) % 32 == 24) ? 0 : 8);          // hi row stride (words) = 8 (mod 16)
+    static constexpr int SL = KT * 4 + (((KT * 4) % 8 == 4) ? 0 : 4);                                  // lo row stride (words) = 4 (mod 8)
+    static constexpr int SA = 12;                                                                      // transpose buffer row stride (words)
+    static constexpr size_t smem_bytes = sizeof(float) * (64 * (SH + SL) + 128 + (kSampleThreads / 32) * 32 * SA);
+};
+
+template <int LMAX, bool NERF, int ND, int MINB, int MLP, bool RUNS>
 __global__ void __launch_bounds__(kSampleThreads, MINB)
 sample_encode_kernel(const __grid_constant__ SampleParams p) {
+    constexpr bool REMAP = MLP == 1, MMA = MLP == 2;
+    static_assert(!(MMA && RUNS), "the tensor-core density layer takes the features from registers");
+    static_assert(LMAX % 2 == 0, "k-tiles of two levels");
+    using ML = MmaLayout<LMAX>;
     constexpr int LC = LMAX * 4;
     constexpr int LDS = LC + 4;  // row stride (floats): 16-byte slots of 8 consecutive rows fall in distinct banks
     extern __shared__ __align__(16) float smem_dyn[];
-    float* sW1 = smem_dyn;                       // [64][LDS]
-    float* sB1 = sW1 + 64 * LDS;                 // [64]
-    float* sW2 = sB1 + 64;                       // [64]
-    float* sF = sW2 + 64;                        // [128][LDS], only allocated for the re-mapped MLP phase / RUNS
+    float* sW1 = smem_dyn;                                   // [64][LDS]   (MMA: hi pairs [64][SH], then lo words [64][SL])
+    float* sB1 = sW1 + 64 * (MMA ? ML::SH + ML::SL : LDS);   // [64]
+    float* sW2 = sB1 + 64;                                   // [64]
+    float* sF = sW2 + 64;                                    // [128][LDS] for the re-mapped phase / RUNS; MMA: [4 warps][32][SA]
     (void)sF;
-    for (int i = threadIdx.x; i < 64 * LMAX; i += kSampleThreads) {
-        const int j = i / LMAX, k4 = i - j * LMAX;
-        *reinterpret_cast<float4*>(sW1 + j * LDS + 4 * k4) = __ldg(reinterpret_cast<const float4*>(p.w1p) + i);
+    if constexpr (MMA) {
+        uint32_t* sWl = reinterpret_cast<uint32_t*>(sW1 + 64 * ML::SH);
+        for (int i = threadIdx.x; i < 64 * ML::KT * 4; i += kSampleThreads) {
+            const int n = i / (ML::KT * 4), r = i - n * (ML::KT * 4), kt = r >> 2, t = r & 3;
+            const float wa = __ldg(p.w1p + n * LC + 8 * kt + t), wb = __ldg(p.w1p + n * LC + 8 * kt + t + 4);
+            const float ha = tf32_hi(wa), hb = tf32_hi(wb);
+            *reinterpret_cast<float2*>(sW1 + n * ML::SH + 8 * kt + 2 * t) = make_float2(ha, hb);
+            sWl[n * ML::SL + 4 * kt + t] = bf16_bits(wa - ha) | (bf16_bits(wb - hb) << 16);
+        }
+    } else {
+        for (int i = threadIdx.x; i < 64 * LMAX; i += kSampleThreads) {
+            const int j = i / LMAX, k4 = i - j * LMAX;
+            *reinterpret_cast<float4*>(sW1 + j * LDS + 4 * k4) = __ldg(reinterpret_cast<const float4*>(p.w1p) + i);
+        }
     }
     if (threadIdx.x < 64) {
         sB1[threadIdx.x] = p.b1[threadIdx.x];
         sW2[threadIdx.x] = p.w2[threadIdx.x];
     }
 
+    if constexpr (MMA) __syncthreads();  // weights staged; the warps run independently from here on
     const size_t block0 = (size_t)blockIdx.x * kSampleThreads;
-    const SamplePos me = sample_pos(block0 + threadIdx.x, p.n_rays, p.S, p.rw_log2);
+    const BlockSamples samples(block0, p.n_rays, p.S, p.rw_log2);
+    const SamplePos me = samples.at(threadIdx.x);
     const size_t idx = (size_t)me.ray * p.S + me.s;  // row of this sample in the [N*S] buffers
     float2 F2[LMAX * 2];  // pooled features, (x,y) / (z,w) pairs per level
 #pragma unroll
@@ -230,7 +301,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
             }
         }
         for (int l = L; l < LMAX; ++l) *reinterpret_cast<float4*>(myF + 4 * l) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (!REMAP) {
+        if constexpr (MLP == 0) {
 #pragma unroll
             for (int l = 0; l < LMAX; ++l) {
                 const float4 f = *reinterpret_cast<const float4*>(myF + 4 * l);
@@ -285,7 +356,104 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
             }
         }
     }
-    if constexpr (!REMAP) {
+    if constexpr (MMA) {
+        // density_layer: Linear(L*C,64) -> ReLU -> Linear(64, .)[0]   (models.py:L438-441, L507-508)
+        constexpr int KT = ML::KT, SH = ML::SH, SL = ML::SL, SA = ML::SA;
+        // hidden units per pass: all 64 (64 accumulator registers) where the register budget is 128, else 2 x 32
+        constexpr int NHALF = (MINB <= UC_MMA_ONE_PASS_MINB) ? 1 : 2, NT = 8 / NHALF;
+        const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+        float* sAw = sF + wq * (32 * SA);                        // this warp's transpose buffer [32 rows][8 columns]
+        const float* Ar = sAw + g * SA + t;                      // A fragment element (row g + 8 i, column t + 4 j)
+        const float2* Wh = reinterpret_cast<const float2*>(sW1 + g * SH) + t;                     // unit 8 nt + g: {hi[t], hi[t + 4]}
+        const uint32_t* Wl = reinterpret_cast<const uint32_t*>(sW1 + 64 * SH) + g * SL + t;       // {lo[t], lo[t + 4]} as bf16 x 2
+        const float2 sixth = make_float2(0.16666667f, 0.16666667f);
+#pragma unroll
+        for (int i = 0; i < LMAX * 2; ++i) F2[i] = fmul2(F2[i], sixth);  // .mean(dim=-3) over the 6 points, models.py:L496
+        float raw[4] = {0.f, 0.f, 0.f, 0.f};                     // rows g, g + 8, 16 + g, 24 + g of the warp's block
+#pragma unroll 1
+        for (int half = 0; half < NHALF; ++half) {
+            float acc[2][NT][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[mt][n][e] = 0.f;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                __syncwarp();                                    // the previous k-tile has been read
+                *reinterpret_cast<float4*>(sAw + lane * SA) = make_float4(F2[4 * kt].x, F2[4 * kt].y, F2[4 * kt + 1].x, F2[4 * kt + 1].y);
+                *reinterpret_cast<float4*>(sAw + lane * SA + 4) =
+                    make_float4(F2[4 * kt + 2].x, F2[4 * kt + 2].y, F2[4 * kt + 3].x, F2[4 * kt + 3].y);
+                __syncwarp();
+                uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // the tensor core reads the upper 19 bits of an operand: hi = those bits, lo = the exact rest
+                        const float x = Ar[(16 * mt + 8 * (e & 1)) * SA + 4 * (e >> 1)];
+                        ah[mt][e] = __float_as_uint(x) & 0xffffe000u;
+                        al[mt][e] = __float_as_uint(x - __uint_as_float(ah[mt][e]));
+                    }
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const int nt = NT * half + n;
+                    const float2 wh = Wh[(8 * nt * SH + 8 * kt) / 2];
+                    const uint32_t wl = Wl[8 * nt * SL + 4 * kt];
+                    const uint32_t bh0 = __float_as_uint(wh.x), bh1 = __float_as_uint(wh.y);
+                    const uint32_t bl0 = wl << 16, bl1 = wl & 0xffff0000u;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {             // small terms first
+                        mma_tf32(acc[mt][n], al[mt], bh0, bh1);
+                        mma_tf32(acc[mt][n], ah[mt], bl0, bl1);
+                        mma_tf32(acc[mt][n], ah[mt], bh0, bh1);
+                    }
+                }
+            }
+            // C fragment: acc[mt][n][2 rh + e] = (row 16 mt + g + 8 rh, unit 8 (NT half + n) + 2 t + e)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const int u = 8 * (NT * half + n) + 2 * t;
+                const float2 b = *reinterpret_cast<const float2*>(sB1 + u), w2 = *reinterpret_cast<const float2*>(sW2 + u);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int rh = 0; rh < 2; ++rh) {
+                        const float a0 = fmaxf(acc[mt][n][2 * rh] + b.x, 0.f), a1 = fmaxf(acc[mt][n][2 * rh + 1] + b.y, 0.f);
+                        acc[mt][n][2 * rh] = a0;
+                        acc[mt][n][2 * rh + 1] = a1;
+                        raw[2 * mt + rh] = fmaf(w2.y, a1, fmaf(w2.x, a0, raw[2 * mt + rh]));
+                    }
+            }
+            if constexpr (NERF) {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int rh = 0; rh < 2; ++rh) {
+                        const SamplePos o = samples.at(32 * wq + 16 * mt + 8 * rh + g);
+                        if (o.valid) {  // columns 16 t + 2 nt + e (h1_col), nt = NT half + n: 2 NT consecutive floats
+                            float* hrow = p.h1 + ((size_t)o.ray * p.S + o.s) * 64 + 16 * t + 2 * NT * half;
+#pragma unroll
+                            for (int n = 0; n < NT; n += 2)
+                                *reinterpret_cast<float4*>(hrow + 2 * n) = make_float4(
+                                    acc[mt][n][2 * rh], acc[mt][n][2 * rh + 1], acc[mt][n + 1][2 * rh], acc[mt][n + 1][2 * rh + 1]);
+                        }
+                    }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            raw[i] += __shfl_xor_sync(0xffffffffu, raw[i], 1);
+            raw[i] += __shfl_xor_sync(0xffffffffu, raw[i], 2);
+        }
+        // lane t of the quad writes the quad's row 16 (t / 2) + 8 (t % 2) + g
+        const float mine = t == 0 ? raw[0] : t == 1 ? raw[1] : t == 2 ? raw[2] : raw[3];
+        const SamplePos o = samples.at(32 * wq + 16 * (t >> 1) + 8 * (t & 1) + g);
+        if (o.valid) p.density[(size_t)o.ray * p.S + o.s] = softplus_f(mine + p.b2 + p.density_bias);  // models.py:L581
+        return;
+    }
+    if constexpr (MLP == 0) {
         // thread-per-sample density layer (weights as broadcast LDS.128); used where the re-mapped phase does not pay
         __syncthreads();  // weights staged
         if (!me.valid) return;
@@ -301,7 +469,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
             float hv[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
-                const int j = ((c + cc) >> 4) + 4 * ((c + cc) & 15);
+                const int j = h1_perm(c + cc);
                 float2 a2 = make_float2(sB1[j], 0.f);  // even / odd partial sums (FFMA2)
                 const float4* wr = reinterpret_cast<const float4*>(sW1 + j * LDS);
 #pragma unroll
@@ -370,11 +538,11 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
         if (NERF) {
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                const SamplePos o = sample_pos(block0 + (size_t)(sg + 32 * s), p.n_rays, p.S, p.rw_log2);
+                const SamplePos o = samples.at(sg + 32 * s);
                 if (o.valid) {
-                    float* hrow = p.h1 + ((size_t)o.ray * p.S + o.s) * 64 + 16 * hg + 8 * half;  // permuted columns
-                    *reinterpret_cast<float4*>(hrow) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
-                    *reinterpret_cast<float4*>(hrow + 4) = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
+                    float* hrow = p.h1 + ((size_t)o.ray * p.S + o.s) * 64;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) hrow[h1_col(hg + 4 * (8 * half + jj))] = acc[s][jj];  // permuted columns
                 }
             }
         }
@@ -386,7 +554,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
     }
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const SamplePos o = sample_pos(block0 + (size_t)(sg + 32 * s), p.n_rays, p.S, p.rw_log2);
+        const SamplePos o = samples.at(sg + 32 * s);
         if (o.valid && hg == s) p.density[(size_t)o.ray * p.S + o.s] = softplus_f(raw[s] + p.b2 + p.density_bias);  // models.py:L581
     }
 }
@@ -412,10 +580,19 @@ static int launch_one_impl(const SampleParams& p, cudaStream_t st) {
     const size_t total = (size_t)div_up(p.n_rays, 32u) * 32u * (size_t)p.S;  // ray groups of 32, see sample_pos
     const unsigned blocks = (unsigned)div_up(total, (size_t)kSampleThreads);
     // measured on B200 (profiles/r1_summary.md): the re-mapped density layer pays on the proposal level only
-    constexpr bool kRemap = UC_REMAP_PROP ? !NERF : false;
-    constexpr size_t smem = sizeof(float) * ((64 + ((kRemap || RUNS) ? kSampleThreads : 0)) * (LMAX * 4 + 4) + 128);
-    UC_ENSURE_SMEM(smem, sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap, RUNS>);
-    sample_encode_kernel<LMAX, NERF, ND, MINB, kRemap, RUNS><<<blocks, kSampleThreads, smem, st>>>(p);
+    constexpr int kFfma = (UC_REMAP_PROP ? !NERF : false) ? 1 : 0;
+    if constexpr (!RUNS) {
+        if (p.mlp_mma) {
+            constexpr size_t smem = MmaLayout<LMAX>::smem_bytes;
+            UC_ENSURE_SMEM(smem, sample_encode_kernel<LMAX, NERF, ND, MINB, 2, RUNS>);
+            sample_encode_kernel<LMAX, NERF, ND, MINB, 2, RUNS><<<blocks, kSampleThreads, smem, st>>>(p);
+            UC_LAUNCH_CHECK();
+            return 0;
+        }
+    }
+    constexpr size_t smem = sizeof(float) * ((64 + ((kFfma || RUNS) ? kSampleThreads : 0)) * (LMAX * 4 + 4) + 128);
+    UC_ENSURE_SMEM(smem, sample_encode_kernel<LMAX, NERF, ND, MINB, kFfma, RUNS>);
+    sample_encode_kernel<LMAX, NERF, ND, MINB, kFfma, RUNS><<<blocks, kSampleThreads, smem, st>>>(p);
     UC_LAUNCH_CHECK();
     return 0;
 }

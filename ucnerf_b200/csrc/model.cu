@@ -497,7 +497,17 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
         UC_REQUIRE(value == 32 || value == 16 || value == 8 || value == 4, "warp_rays_*: 32, 16, 8 or 4 rays per warp");
         m->warp_rays_log2[k == "warp_rays_nerf" ? 1 : 0] = value == 32 ? 5 : value == 16 ? 4 : value == 8 ? 3 : 2;
     }
-    else if (k == "timing") m->timing = value != 0;
+    else if (k == "timing") {
+        m->timing = value != 0;
+        // events are created here, not inside the region the caller is about to time (cudaEventCreate occasionally takes
+        // milliseconds); 512 pairs cover 18 frames of 4 chunks between two ucnerf_get_timing calls
+        while (m->timing && m->pool.size() < 512) {
+            cudaEvent_t a, b;
+            UC_CUDA_OK(cudaEventCreate(&a));
+            UC_CUDA_OK(cudaEventCreate(&b));
+            m->pool.emplace_back(a, b);
+        }
+    }
     else if (k == "tc_debug") m->tc_debug = (uint32_t)value;  // profiling experiments (results invalid when != 0)
     else { set_error("set_option: unknown key " + k); return 1; }
     return 0;

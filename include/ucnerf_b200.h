@@ -289,8 +289,11 @@ int ucnerf_render_camera_host(ucnerf_model* m, const ucnerf_camera* cam, uint32_
 /* Number of kernels launched by this library in this process so far (bench.py's gpu_launches). */
 uint64_t ucnerf_launch_count(void);
 
-/* Tunables: "chunk_rays" (rays per internal chunk), "color_mlp" (0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = auto:
- * tensor cores whenever the MLP widths allow, the default), "timing" (see ucnerf_get_timing). */
+/* Tunables: "chunk_rays" (rays per internal chunk), "color_mlp" (0 = fp32 SIMT, 1 = tcgen05 FP16 3-term split, 2 = auto:
+ * tensor cores whenever the MLP widths allow, the default), "timing" (see ucnerf_get_timing), "encode_mlp_mma" (density
+ * layer of the sample/encode kernel as mma.sync 3xTF32: bit 0 = proposal levels, bit 1 = NeRF level, default 3; 0 = the
+ * fp32 FMA forms), "encode_runs" (cell-run reuse of gathered corners, bit-identical, default 0; implies the FMA forms),
+ * "warp_rays_prop" / "warp_rays_nerf" (rays per warp of that kernel: 32, 16, 8 or 4). */
 int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value);
 
 /* Brightness-correction head folded into the compositing epilogue.  The reference evaluates

@@ -180,6 +180,32 @@ def test_density_layer_on_tensor_cores_matches_fp32_form(name):
     assert not bad, bad
 
 
+def test_density_layer_on_tensor_cores_every_level_count():
+    """The kernel instantiations not covered by the named cases (padded level counts 4 and 16, and a level count that is
+    smaller than its padding): tensor-core density layer against the FFMA form on the same weights and rays."""
+    cfg = O.HotPathConfig(num_prop_samples=32, num_nerf_samples=16, prop_grids=[O.GridSpec(64), O.GridSpec(65536)],
+                          nerf_grid=O.GridSpec(1024))
+    assert [g.num_levels for g in cfg.prop_grids] + [cfg.nerf_grid.num_levels] == [3, 13, 7]
+    params = O.init_params(cfg, seed=11)
+    r = build_renderer(cfg, params)
+    batch = O.synthetic_rays(1031, seed=12)
+    outs = {}
+    for mode in (0, 3):
+        r.set_option("encode_mlp_mma", mode)
+        outs[mode] = run(r, batch)
+    d0, d1 = outs[0]["sample_density"], outs[3]["sample_density"]
+    assert float(np.max(np.abs(d0 - d1) / (np.abs(d0) + 1e-3))) < 2e-4
+    for k in ("rgb", "acc", "sample_rgb", "weights_0", "weights_1", "sdist_2"):
+        assert float(np.max(np.abs(outs[0][k] - outs[3][k]))) < 5e-5, k
+    # and against the oracle: level 12 of the 13-level grid has resolution + 1 = 65537, whose 32-bit stride product
+    # wraps in the reference kernel (gridencoder.cu:L72-77) - the level is indexed with wrapped strides modulo the table
+    small = {k: v[:48] for k, v in batch.items()}
+    rend, _ = O.model_forward(params, cfg, small)
+    got = run(r, small)
+    for k in ("rgb", "acc"):
+        assert float(np.max(np.abs(got[k] - rend[-1][k].numpy().reshape(got[k].shape)))) < TOL, k
+
+
 def test_full_size_properties():
     """65,536 rays with waymo.gin shapes (10.5 M ray-samples): invariants the domain offers."""
     cfg, params, _, r = case("waymo")

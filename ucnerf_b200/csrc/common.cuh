@@ -128,8 +128,17 @@ inline void make_grid_level(GridLevel& g, int l, int32_t off0, int32_t off1, flo
     g.pow2_mask = (g.hashmap_size & (g.hashmap_size - 1)) == 0 ? g.hashmap_size - 1 : 0u;
     if (g.hashmap_size == 1) g.pow2_mask = 0;
     g.grid_size = (float)grid_size;
-    // dense index of an in-range point: max = (res+1)^3 - 1 < hashmap_size  => no modulo needed
-    if (!g.hashed) g.mod_mode = 0;
+    // dense index of an in-range point: max = (res+1)^3 - 1 < hashmap_size  => no modulo needed.  The stride product
+    // above is 32-bit like the reference's (gridencoder.cu:L72-77): for resolution + 1 >= 65537 it wraps, a level can
+    // then look dense although (res+1)^3 exceeds the table; the reference indexes such a level with the wrapped
+    // strides and reduces modulo the table size - so do we (same stride1 / stride2 arithmetic, mod_mode != 0).
+    bool fits = true;
+    uint64_t full = 1;
+    for (int d = 0; d < 3 && fits; ++d) {
+        full *= (uint64_t)(resolution + 1);
+        fits = full <= (uint64_t)g.hashmap_size;
+    }
+    if (!g.hashed && fits) g.mod_mode = 0;
     else g.mod_mode = g.pow2_mask ? 1u : 2u;
 }
 

@@ -282,8 +282,8 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
                     if ((inmask >> j) & 1u) {
                         const CellCoords c = cell_of(lv, gq[j]);
                         if (c.ix != pix || c.iy != piy || c.iz != piz) {
-                            if (!lv.hashed) gather8<0>(lv, tab, c, v);
-                            else if (lv.mod_mode == 1) gather8<1>(lv, tab, c, v);
+                            if (!lv.hashed && lv.mod_mode == 0) gather8<0>(lv, tab, c, v);
+                            else if (lv.hashed && lv.mod_mode == 1) gather8<1>(lv, tab, c, v);
                             else gather8<2>(lv, tab, c, v);
                             pix = c.ix; piy = c.iy; piz = c.iz;
                         }
@@ -569,7 +569,7 @@ int sample_encode_lmax(int L) {
 // number of leading dense levels if the remaining ones are hashed with power-of-two tables, else -1
 static int dense_prefix(const GridDesc& g) {
     int nd = 0;
-    while (nd < g.num_levels && !g.lv[nd].hashed) ++nd;
+    while (nd < g.num_levels && !g.lv[nd].hashed && g.lv[nd].mod_mode == 0) ++nd;
     for (int l = nd; l < g.num_levels; ++l)
         if (!g.lv[l].hashed || g.lv[l].mod_mode != 1) return -1;
     return nd;

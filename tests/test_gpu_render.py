@@ -97,6 +97,19 @@ def test_render_matches_oracle_on_fresh_rays(name, n, seed):
     assert all(v < TOL for v in err.values()), err
 
 
+@pytest.mark.parametrize("n", [0, 1, 31, 33])
+def test_ragged_and_empty_batches(n):
+    """Batches that do not fill a warp / a 128-row tile, and the empty batch: same pixels as the same rays inside a larger
+    batch (every ray is independent), no launch for n = 0."""
+    cfg, params, _, r = case("waymo")
+    big = O.synthetic_rays(64, seed=21)
+    ref = run(r, big)
+    out = run(r, {k: v[:n] for k, v in big.items()})
+    for k in ("rgb", "acc", "depth", "sample_density", "weights_0"):
+        assert out[k].shape[0] == n, k
+        assert np.array_equal(out[k], ref[k][:n]), k
+
+
 def test_host_entry_equals_device_entry():
     """ucnerf_render_rays_host (H2D + render + D2H inside the call) returns exactly the device-entry results."""
     cfg, params, batch, r = case("waymo")

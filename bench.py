@@ -455,12 +455,14 @@ def run_ours(args):
             if peer is None:
                 for k in dev_in:
                     dev_in[k].copy_(pin2[k], non_blocking=True)
-            if peer is not None:      # H2D of chunk c + 1 under chunk c's kernels, tiles written to every rank's image
-                img = peer.render_host(r, pin, 1.0, start)
+            if peer is not None:
+                # H2D of chunk c + 1 and D2H of this rank's rows of chunk c - 1 under chunk c's kernels; the tiles are
+                # written to every rank's image by the compositing kernel; the all-reduce closes the frame
+                peer.render_host(r, pin, 1.0, start, want=("packed",), out=out_h)
             else:
                 o = r.render_rays(dev_in, 1.0, dev_in["rand_vec"], ("packed",))
                 img = R.gather_tiles(o["packed"], world, world * n)
-            out_h["packed"].copy_(img[start:stop], non_blocking=True)
+                out_h["packed"].copy_(img[start:stop], non_blocking=True)
             torch.cuda.current_stream().synchronize()
     with Clocks(rank, local) as ck:
         ms_e2e = timed(cx, e2e_step, args.steps, max(1, min(args.warmup, 2)))
@@ -468,7 +470,9 @@ def run_ours(args):
            "h2d_bytes_per_step": int(n * 18 * 4), "d2h_bytes_per_step": int(n * PACKED_WIDTH * 4),
            "ms_per_step": ms_e2e / args.steps, "clocks": ck.result,
            "api": "ucnerf_render_rays_host (C ABI, pinned host buffers; H2D of chunk c+1 and D2H of chunk c-1 overlap chunk c)"
-                  if world == 1 else "pinned host rays -> render_rays -> render.gather_tiles (1 all-gather) -> own tile D2H"}
+                  if world == 1 else ("peer.PeerImage.render_host: ucnerf_render_rays_host with the tile exchange fused into the compositing "
+                                     "kernel; own rows back to pinned host memory chunk by chunk" if peer is not None else
+                                     "pinned host rays -> render_rays -> render.gather_tiles (1 all-gather) -> own tile D2H")}
     checksum = float(out_h["packed"][:, :3].double().mean())
 
     line_extra = {}

@@ -100,15 +100,17 @@ class PeerImage:
         self.dist.all_reduce(self._flag, group=self.group)      # frame complete on every rank (see module docstring)
         return self.images[b], out
 
-    def render_host(self, renderer, host_batch, train_frac, row0: int):
+    def render_host(self, renderer, host_batch, train_frac, row0: int, want=(), out=None):
         """Same with the ray batch in (pinned) HOST memory: the library's chunk pipeline copies chunk c + 1 in while chunk c
         renders (ucnerf_render_rays_host), the compositing kernel writes the tiles to every rank's image.  Returns the
-        image; the call has synchronised the render stream before the all-reduce is enqueued."""
+        image; the call has synchronised the render stream before the all-reduce is enqueued.
+        `want` / `out` (pinned host tensors): outputs of THIS rank's tile copied back by the same pipeline, chunk c - 1
+        under chunk c's kernels - N ranks then do not all start a whole-tile device-to-host copy at the frame's end."""
         b = self.frame % len(self.images)
         self.frame += 1
         _lib.check(self.lib.ucnerf_set_peer_targets(renderer._handle, self.world, self._tables[b], int(row0)), "set_peer_targets")
         try:
-            renderer.render_rays_host(host_batch, train_frac, want=(), out={})
+            renderer.render_rays_host(host_batch, train_frac, want=tuple(want), out=out if out is not None else {})
         finally:
             _lib.check(self.lib.ucnerf_set_peer_targets(renderer._handle, 0, None, 0), "set_peer_targets")
         self.dist.all_reduce(self._flag, group=self.group)

@@ -290,3 +290,27 @@ def test_cuda_full_training_size_properties(case):
     lhs = float(prod.sum())
     rhs = float((enc.embeddings.detach().double() * enc.embeddings.grad.double()).sum())
     assert abs(lhs - rhs) <= 1e-5 * float(prod.abs().sum()), (lhs, rhs)
+
+
+def test_level_whose_stride_product_wraps_is_indexed_like_the_reference_on_cpu(harness):
+    """desired_resolution 65536 -> level 12 has resolution + 1 = 65537: the reference's 32-bit stride product wraps
+    (gridencoder.cu:L72-77), the level then counts as dense although it does not fit its table and the index is reduced
+    modulo the table size.  The product's level descriptor (make_grid_level) + pooled_level_forward against the oracle."""
+    gs = O.GridSpec(65536)
+    assert gs.num_levels == 13
+    cfg = O.HotPathConfig(prop_grids=[gs], nerf_grid=O.GridSpec(64))
+    params = O.init_params(cfg, seed=5)
+    gen = torch.Generator().manual_seed(6)
+    means = (torch.rand((40, 6, 3), generator=gen) * 2 - 1) * 0.9
+    stds = torch.rand((40, 6), generator=gen) * 1e-3 + 1e-4
+    feats, coord, _, _ = O.pooled_encode_forward(params, "prop_mlp_0", gs, means, stds)
+    got, gcoord, _ = _harness_run(harness, params, "prop_mlp_0", gs, means.numpy(), stds.numpy(),
+                                  np.zeros((40, gs.num_levels * 4), np.float32))
+    ref = feats.numpy().reshape(40, gs.num_levels, 4)
+    err = np.abs(got.reshape(ref.shape) - ref).max(axis=(0, 2))
+    assert err[:11].max() < 1e-5, err
+    # levels 11 and 12: pos = x * 65535 + 0.5 leaves 7 - 8 fraction bits in fp32, so the rounding of that one operation
+    # (fused or not) moves the interpolation weights by up to 2^-7; a wrongly indexed entry would be off by the table
+    # amplitude (0.5) times the erf weight (about 0.06 here), a hundred times the bar
+    assert err[11:].max() < 1e-3, err
+    assert np.abs(ref[:, 12]).mean() > 3e-3

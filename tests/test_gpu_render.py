@@ -219,6 +219,19 @@ def test_density_layer_on_tensor_cores_every_level_count():
         assert float(np.max(np.abs(got[k] - rend[-1][k].numpy().reshape(got[k].shape)))) < TOL, k
 
 
+def test_odd_sample_counts_match_oracle():
+    """Sample counts that are not multiples of 4 (a 128-thread block of the encode kernel then straddles ray groups, a
+    128-row tile of the colour MLP straddles rays at odd offsets): pixels against the oracle."""
+    cfg = O.HotPathConfig(num_prop_samples=37, num_nerf_samples=19)
+    params = O.init_params(cfg, seed=31)
+    r = build_renderer(cfg, params)
+    batch = O.synthetic_rays(77, seed=32)
+    rend, _ = O.model_forward(params, cfg, batch)
+    got = run(r, batch)
+    for k in ("rgb", "acc", "depth_raw"):
+        assert float(np.max(np.abs(got[k] - rend[-1][k].numpy().reshape(got[k].shape)))) < TOL, k
+
+
 def test_full_size_properties():
     """65,536 rays with waymo.gin shapes (10.5 M ray-samples): invariants the domain offers."""
     cfg, params, _, r = case("waymo")

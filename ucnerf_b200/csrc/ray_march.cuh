@@ -156,9 +156,10 @@ float sky_tc_act_scale();
 void sky_tc_pack_chunk(const float* wt_rows, int n_cols, float scale, uint8_t* dst);
 int sample_encode_lmax(int L);
 // h1 column c holds hidden unit h1_perm(c) of density_layer.0 (layout written by sample_encode_kernel): lane t of a
-// quad owns the accumulator columns {8 nt + 2 t + e} of the mma.sync C fragments, stored as 16 consecutive floats
-// -> column 16 t + 2 nt + e.  h1_col is the inverse.
-__host__ __device__ inline int h1_perm(int c) { return 8 * ((c % 16) / 2) + 2 * (c / 16) + (c % 2); }
-__host__ __device__ inline int h1_col(int u) { return 16 * ((u % 8) / 2) + 2 * (u / 8) + (u % 2); }
+// quad owns the accumulator columns {8 nt + 2 t + e} of the mma.sync C fragments.  They are stored as two 32-byte pieces
+// (nt < 4 / nt >= 4) at columns 32 (nt / 4) + 8 t + 2 (nt % 4) + e, so that one 256-bit store instruction of a quad covers
+// one whole 128-byte line of the row.  h1_col is the inverse.
+__host__ __device__ inline int h1_perm(int c) { return 8 * (4 * (c / 32) + (c % 8) / 2) + 2 * ((c % 32) / 8) + (c % 2); }
+__host__ __device__ inline int h1_col(int u) { return 32 * (u / 32) + 8 * ((u % 8) / 2) + 2 * ((u / 8) % 4) + (u % 2); }
 
 }  // namespace ucnerf

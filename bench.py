@@ -21,6 +21,7 @@ One JSON line is printed by rank 0.  Besides the contract keys it carries (each 
   gpu_reference             the reference's own Python + its own CUDA kernel (sm_100a build) on this same GPU
   cpu_baseline              the reference's own Python + C/OpenMP grid kernel on the host cores (bounded sample)."""
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -59,50 +60,105 @@ def parse():
     ap.add_argument("--encode-runs", type=int, default=-1, help="A/B: cell-run reuse in the encode kernel (bit0 prop, bit1 NeRF); -1 = library default")
     ap.add_argument("--heads", action="store_true", help="alias of --extras ...,with_heads")
     ap.add_argument("--option", action="append", default=[], help="key=int library option (A/B experiments)")
+    ap.add_argument("--ray-tile-width", default="image", help="'image' (default): tell the library that the ray batch is a row-major "
+                    "image of the workload's width (option ray_tile_width: 4x8-pixel patches per warp, bit-identical results); 0 = off")
     ap.add_argument("--tc-debug", type=int, default=0, help="profiling experiment flags for the TC kernel (invalid results)")
     return ap.parse_args()
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  Read through NVML
+    inside this process (what nvidia-smi itself queries) every 50 ms: spawning an nvidia-smi process five times a second
+    next to the timed steps occasionally cost the steps tens of milliseconds on a fresh box.  NVML is initialised and
+    queried once BEFORE the region (`prime`); nvidia-smi remains the fallback where pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+    _nvml = None        # (module, {gpu index: handle}) once primed; False if unavailable
+
+    @classmethod
+    def prime(cls, gpu_index=0):
+        """Initialise NVML and resolve the device handle (by PCI bus id of the CUDA device, so CUDA_VISIBLE_DEVICES does not
+        matter); one query, so that the first-call cost is paid outside every timed region."""
+        if cls._nvml is False:
+            return None
+        try:
+            if cls._nvml is None:
+                import pynvml
+                pynvml.nvmlInit()
+                cls._nvml = (pynvml, {})
+            nv, handles = cls._nvml
+            if gpu_index not in handles:
+                try:
+                    pr = torch.cuda.get_device_properties(gpu_index)
+                    bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                    handles[gpu_index] = nv.nvmlDeviceGetHandleByPciBusId(bus.encode())
+                except Exception:
+                    handles[gpu_index] = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+                h = handles[gpu_index]          # first calls of every query used later (they are the slow ones)
+                nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            return handles[gpu_index]
+        except Exception:
+            cls._nvml = False
+            return None
 
     def __init__(self, gpu_index=0):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []          # (sm MHz, max sm MHz, set of reasons)
+        self.handle = self.prime(gpu_index)
         self._stop_evt = threading.Event()
+        self.first_done = threading.Event()
+
+    def _sample_nvml(self):
+        nv = self._nvml[0]
+        sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        self.rows.append((float(sm), float(mx), {n for n, b in self.REASONS if mask & b}))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                              str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            r = [c.strip() for c in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            self.rows.append((float(r[1]), float(r[2]), {n for n, v in zip(names, r[5:9]) if v.lower().startswith("active")}))
 
     def run(self):
+        first = True
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.handle is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            if first:       # taken before the caller's timed region starts (Clocks.__enter__ waits for it); dropped in stop()
+                first = False
+                self.first_done.set()
+            self._stop_evt.wait(0.05 if self.handle is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        sm.sort()
+        if len(self.rows) > 1:
+            self.rows = self.rows[1:]       # the priming sample was taken on an idle GPU
+        sm = sorted(r[0] for r in self.rows)
+        mx = [r[1] for r in self.rows]
+        reasons = set().union(*[r[2] for r in self.rows]) if self.rows else set()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.handle is not None else "nvidia-smi"}
 
 
 class Clocks:
@@ -113,11 +169,17 @@ class Clocks:
         self.result = None
 
     def __enter__(self):
+        # everything that can stall the launching thread happens here, before the caller synchronises and starts its clock:
+        # thread start, the sampler's first driver query, a full garbage collection (then none until __exit__)
         if self.s:
             self.s.start()
+            self.s.first_done.wait(2.0)
+        gc.collect()
+        gc.disable()
         return self
 
     def __exit__(self, *a):
+        gc.enable()
         if self.s:
             self.result = self.s.stop()
 
@@ -352,6 +414,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     cx.dev = dev = torch.device(f"cuda:{local}")
+    if rank == 0:
+        ClockSampler.prime(local)        # NVML initialised and queried once, well before any timed region
     t_start = time.perf_counter()
     if args.extras == "default":
         extras = set(EXTRAS_1 if world == 1 else EXTRAS_N)
@@ -378,6 +442,9 @@ def run_ours(args):
         r.set_option("tc_debug", args.tc_debug)
     if args.encode_runs >= 0:
         r.set_option("encode_runs", args.encode_runs)
+    tile_w = wl.width if args.ray_tile_width == "image" else int(args.ray_tile_width)
+    if tile_w and wl.width % 4 == 0:
+        r.set_option("ray_tile_width", tile_w)     # the batch below is that frame, row-major (as render_image passes it)
     for kv in args.option:
         k, v = kv.split("=")
         r.set_option(k, int(v))
@@ -571,7 +638,7 @@ def run_ours(args):
                        "samples_per_ray": spr, "prop_samples": wl.num_prop_samples, "nerf_samples": wl.num_nerf_samples,
                        "grid_levels": [wl.grid_levels(d) for d in wl.prop_desired] + [wl.grid_levels(wl.nerf_desired)],
                        "log2_hashmap_size": wl.log2_hashmap_size, "parallelism": f"ray-tile x{world}, replicated model",
-                       "cameras": args.cameras,
+                       "cameras": args.cameras, "ray_tile_width": tile_w if wl.width % 4 == 0 else 0,
                        "collective": ("none" if world == 1 else
                                       "fused: compositing kernel stores the packed tiles into every rank's image over NVLink "
                                       "peer memory (peer.PeerImage) + one 4-byte all_reduce per step" if peer is not None else

@@ -79,6 +79,7 @@ struct ucnerf_model {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host entry: H2D / D2H overlap the render stream chunk by chunk
     std::vector<cudaEvent_t> ev_in, ev_done;
     int64_t chunk_rays = 131072;
+    int64_t ray_tile_width = 0;  // > 0: ray batches are whole rows of a row-major image of this width (see SampleParams::tile_w)
     int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 FP16 split (error if shapes unsupported), 2 = auto
     bool use_affine = false;
     float affine[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};   // BrightnessCorrection affine of the current image (row-major 3x4)
@@ -306,7 +307,7 @@ static int resolve_timing(ucnerf_model* m) {
 }
 
 static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_t ray0, double train_frac,
-                        const ucnerf_outputs& o, cudaStream_t st) {
+                        const ucnerf_outputs& o, cudaStream_t st, uint64_t tile_w) {
     const ucnerf_model_desc& d = m->d;
     RayPtrs rp{r.origins + 3 * ray0, r.directions + 3 * ray0, r.viewdirs + 3 * ray0, r.cam_dirs + 3 * ray0,
                r.radii + ray0, r.near + ray0, r.far + ray0, r.rand_vec + 3 * ray0};
@@ -367,6 +368,7 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         std::memcpy(sp.g2, ls.g2, sizeof(sp.g2));
         sp.cell_runs = (m->encode_runs >> (nerf ? 1 : 0)) & 1;
         sp.mlp_mma = (m->encode_mlp_mma >> (nerf ? 1 : 0)) & 1;
+        sp.tile_w = (tile_w > 0 && ray0 % (size_t)tile_w == 0) ? (uint32_t)tile_w : 0u;
         sp.rw_log2 = m->warp_rays_log2[nerf ? 1 : 0];
         if (S % (32 >> sp.rw_log2) != 0) sp.rw_log2 = 5;   // sample blocks must tile S
         float* rgb_s = nullptr;
@@ -490,6 +492,10 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
     UC_REQUIRE(m && key, "set_option: null argument");
     const std::string k(key);
     if (k == "chunk_rays") { UC_REQUIRE(value >= 1, "chunk_rays must be >= 1"); m->chunk_rays = value; }
+    else if (k == "ray_tile_width") {
+        UC_REQUIRE(value >= 0 && value % 4 == 0 && value <= (1 << 20), "ray_tile_width: image width, a multiple of 4 (0 = off)");
+        m->ray_tile_width = value;
+    }
     else if (k == "color_mlp") { UC_REQUIRE(value >= 0 && value <= 2, "color_mlp: 0 = fp32 SIMT, 1 = tensor core, 2 = auto"); m->color_mode = (int)value; }
     else if (k == "encode_runs") { UC_REQUIRE(value >= 0 && value <= 3, "encode_runs: bit 0 = proposal levels, bit 1 = NeRF level"); m->encode_runs = (int)value; }
     else if (k == "encode_mlp_mma") { UC_REQUIRE(value >= 0 && value <= 3, "encode_mlp_mma: bit 0 = proposal levels, bit 1 = NeRF level"); m->encode_mlp_mma = (int)value; }
@@ -547,8 +553,26 @@ extern "C" int ucnerf_get_timing(ucnerf_model* m, float* ms_out5, uint32_t* laun
     return 0;
 }
 
+namespace ucnerf {
+// rays per internal chunk: with ray_tile_width set, a whole number of 8-row bands, so that every chunk starts on an image row
+static uint64_t effective_chunk(const ucnerf_model* m, uint64_t tile_w) {
+    const uint64_t c = (uint64_t)m->chunk_rays, band = 8u * tile_w;
+    if (band == 0 || c < band) return c;
+    return c / band * band;
+}
+}  // namespace ucnerf
+
+static int render_rays_tiled(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays* rays, double train_frac,
+                             const ucnerf_outputs* out, void* stream, int64_t tile_w_or_option);
+
 extern "C" int ucnerf_render_rays(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays* rays, double train_frac,
                                   const ucnerf_outputs* out, void* stream) {
+    return render_rays_tiled(m, n_rays, rays, train_frac, out, stream, -1);
+}
+
+// tile_w_or_option: image width of the row-major ray batch (0 = unknown), -1 = the model's "ray_tile_width" option
+static int render_rays_tiled(ucnerf_model* m, uint64_t n_rays, const ucnerf_rays* rays, double train_frac,
+                             const ucnerf_outputs* out, void* stream, int64_t tile_w_or_option) {
     UC_REQUIRE(m && rays && out, "render_rays: null argument");
     if (n_rays == 0) return 0;
     UC_REQUIRE(rays->origins && rays->directions && rays->viewdirs && rays->cam_dirs && rays->radii && rays->near &&
@@ -556,9 +580,11 @@ extern "C" int ucnerf_render_rays(ucnerf_model* m, uint64_t n_rays, const ucnerf
                "render_rays: every ray array (incl. rand_vec) must be provided");
     std::lock_guard<std::mutex> lk(m->mu);
     cudaStream_t st = (cudaStream_t)stream;
-    for (uint64_t r0 = 0; r0 < n_rays; r0 += (uint64_t)m->chunk_rays) {
-        const uint32_t n = (uint32_t)std::min<uint64_t>((uint64_t)m->chunk_rays, n_rays - r0);
-        if (int e = render_chunk(m, n, *rays, (size_t)r0, train_frac, *out, st)) return e;
+    const uint64_t tile_w = (uint64_t)(tile_w_or_option < 0 ? m->ray_tile_width : tile_w_or_option);
+    const uint64_t chunk = effective_chunk(m, tile_w);
+    for (uint64_t r0 = 0; r0 < n_rays; r0 += chunk) {
+        const uint32_t n = (uint32_t)std::min<uint64_t>(chunk, n_rays - r0);
+        if (int e = render_chunk(m, n, *rays, (size_t)r0, train_frac, *out, st, tile_w)) return e;
     }
     return 0;
 }
@@ -640,13 +666,13 @@ static int camera_rays(ucnerf_model* m, const ucnerf_camera* cam, uint32_t row0,
 // c-1 run on their own streams under chunk c's kernels.  The caller holds m->mu.
 static int render_pipelined(ucnerf_model* m, size_t N, const ucnerf_rays& rd, const float* const* srcs, float* const* dsts,
                             const size_t* widths, double train_frac, const ucnerf_outputs& od, std::vector<OutSlot>& slots,
-                            cudaStream_t st) {
+                            cudaStream_t st, uint64_t tile_w) {
     // ---- chunk pipeline: the copies of chunk c+1 (in) and c-1 (out) run on their own streams under chunk c's kernels ----
     if (!m->copy_in) {
         UC_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_in, cudaStreamNonBlocking));
         UC_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_out, cudaStreamNonBlocking));
     }
-    const size_t chunk = (size_t)m->chunk_rays;
+    const size_t chunk = (size_t)effective_chunk(m, tile_w);
     const size_t nchunks = (N + chunk - 1) / chunk;
     while (m->ev_in.size() < nchunks + 1) {
         cudaEvent_t a, b;
@@ -670,7 +696,7 @@ static int render_pipelined(ucnerf_model* m, size_t N, const ucnerf_rays& rd, co
     for (size_t c = 0; c < nchunks; ++c) {
         const size_t r0 = c * chunk, n = std::min(chunk, N - r0);
         UC_CUDA_OK(cudaStreamWaitEvent(st, m->ev_in[c], 0));
-        if (int e = render_chunk(m, (uint32_t)n, rd, r0, train_frac, od, st)) return e;
+        if (int e = render_chunk(m, (uint32_t)n, rd, r0, train_frac, od, st, tile_w)) return e;
         UC_CUDA_OK(cudaEventRecord(m->ev_done[c], st));
         UC_CUDA_OK(cudaStreamWaitEvent(m->copy_out, m->ev_done[c], 0));
         for (auto& sl : slots) {
@@ -710,7 +736,7 @@ extern "C" int ucnerf_render_camera(ucnerf_model* m, const ucnerf_camera* cam, u
         std::lock_guard<std::mutex> lk(m->mu);
         if (int e = camera_rays(m, cam, row0, n_rows, rd, (cudaStream_t)stream)) return e;
     }
-    return ucnerf_render_rays(m, (uint64_t)n_rows * cam->width, &rd, train_frac, out, stream);
+    return render_rays_tiled(m, (uint64_t)n_rows * cam->width, &rd, train_frac, out, stream, cam->width % 4 == 0 ? (int64_t)cam->width : 0);
 }
 
 extern "C" int ucnerf_render_camera_host(ucnerf_model* m, const ucnerf_camera* cam, uint32_t row0, uint32_t n_rows,
@@ -725,7 +751,7 @@ extern "C" int ucnerf_render_camera_host(ucnerf_model* m, const ucnerf_camera* c
     if (int e = stage_outputs(m, N, oh, od, slots)) return e;
     ucnerf_rays rd{};
     if (int e = camera_rays(m, cam, row0, n_rows, rd, st)) return e;      // one kernel on the render stream
-    if (int e = render_pipelined(m, N, rd, nullptr, nullptr, nullptr, train_frac, od, slots, st)) return e;
+    if (int e = render_pipelined(m, N, rd, nullptr, nullptr, nullptr, train_frac, od, slots, st, cam->width % 4 == 0 ? cam->width : 0)) return e;
     slots.clear();
     return copy_back_and_check(m, slots, st);
 }
@@ -754,7 +780,7 @@ extern "C" int ucnerf_render_rays_host(ucnerf_model* m, uint64_t n_rays, const u
     ucnerf_outputs od{};
     std::vector<OutSlot> slots;
     if (int e = stage_outputs(m, N, oh, od, slots)) return e;
-    if (int e = render_pipelined(m, N, rd, srcs, dsts, widths, train_frac, od, slots, st)) return e;
+    if (int e = render_pipelined(m, N, rd, srcs, dsts, widths, train_frac, od, slots, st, (uint64_t)m->ray_tile_width)) return e;
     slots.clear();
     return copy_back_and_check(m, slots, st);
 }

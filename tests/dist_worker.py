@@ -19,6 +19,10 @@ class FakeRenderer:
     """Same surface as HotPathModel.render_rays, on CPU: outputs are simple functions of the ray origin."""
     num_levels, samples, vis_num_rays = 2, [8, 4], 4
     device = torch.device("cpu")
+    options = {}
+
+    def set_option(self, key, value):          # render_image announces the row length of an image tile and takes it back
+        FakeRenderer.options[key] = int(value)
 
     def render_rays(self, batch, train_frac, rand_vec, want):
         o = batch["origins"]
@@ -98,6 +102,23 @@ def main():
         assert img["weights"].shape == (H, W, 4) and torch.equal(img["weights"][..., 0], origins[..., 0])
         assert img["coord"].shape == (H, W, 4, 3) and torch.equal(img["coord"][:, :, 2, :], origins * 0.5)
         assert len(img["ray_sdist"]) == 2 and img["ray_rgbs"][0].shape == (4, 8, 3)
+        assert "ray_tile_width" not in FakeRenderer.options        # 53 pixels per row: no patch mapping announced
+        # an image whose per-rank tiles start on rows (8 x 16 pixels over 2 ranks): the row length is announced for the tile's
+        # render and taken back before the vis-ray render
+        seen = []
+
+        class Tiled(FakeRenderer):
+            def render_rays(self, batch, train_frac, rand_vec, want):
+                seen.append((batch["origins"].shape[0], FakeRenderer.options.get("ray_tile_width", 0)))
+                return super().render_rays(batch, train_frac, rand_vec, want)
+
+        o2 = torch.rand((8, 16, 3), generator=g)
+        b2 = {k: o2 for k in ("origins", "directions", "viewdirs", "cam_dirs")}
+        b2.update({k: o2[..., :1] for k in ("radii", "near", "far")})
+        img2 = R.render_image(None, Acc(), b2, False, 1.0, Cfg(), renderer=Tiled(), rand_vec=torch.zeros(128, 3))
+        assert torch.equal(img2["rgb"], o2)
+        if 128 % world == 0 and (128 // world) % 16 == 0:
+            assert seen[0] == (128 // world, 16) and seen[1][1] == 0 and FakeRenderer.options["ray_tile_width"] == 0, seen
         # heads of the shipped config on top (sky through the reference-module path, brightness affines): the sharded
         # result must equal the single-process one
         class HCfg(Cfg):

@@ -110,8 +110,9 @@ def test_ragged_and_empty_batches(n):
         assert np.array_equal(out[k], ref[k][:n]), k
 
 
-@pytest.mark.parametrize("width,n", [(8, 4099), (12, 960), (800, 4099), (64, 64 * 24 + 5)])
-def test_image_patch_warp_mapping_is_bit_identical(width, n):
+@pytest.mark.parametrize("width,n,shapes", [(8, 4099, (4, 4)), (12, 960, (4, 0)), (800, 4099, (0, 4)), (64, 64 * 24 + 5, (16, 8)),
+                                            (48, 48 * 19, (8, 16))])
+def test_image_patch_warp_mapping_is_bit_identical(width, n, shapes):
     """Option ray_tile_width: the encode kernel's warps take 4 x 8 pixel patches of a row-major image instead of 32 pixels
     of a row.  Only the assignment of rays to warps changes - every output of every ray is bit-identical, also for batches
     that end inside a band of 8 rows or inside a row, and across internal chunks."""
@@ -120,10 +121,14 @@ def test_image_patch_warp_mapping_is_bit_identical(width, n):
     ref = run(r, batch)
     try:
         r.set_option("ray_tile_width", width)
+        r.set_option("ray_tile_prop", shapes[0])  # patch width per level kind: 4 x 8, 8 x 4 or 16 x 2 pixels, 0 = rows
+        r.set_option("ray_tile_nerf", shapes[1])
         r.set_option("chunk_rays", 1500)          # several chunks, rounded down to whole bands inside the library
         got = run(r, batch)
     finally:
         r.set_option("ray_tile_width", 0)
+        r.set_option("ray_tile_prop", 0)
+        r.set_option("ray_tile_nerf", 4)
         r.set_option("chunk_rays", 131072)
     for k in ("rgb", "acc", "depth", "sample_density", "sample_rgb", "weights_0", "weights_1", "sdist_1"):
         assert np.array_equal(got[k], ref[k]), k

@@ -80,6 +80,7 @@ struct ucnerf_model {
     std::vector<cudaEvent_t> ev_in, ev_done;
     int64_t chunk_rays = 131072;
     int64_t ray_tile_width = 0;  // > 0: ray batches are whole rows of a row-major image of this width (see SampleParams::tile_w)
+    int ray_tile_patch[2] = {0, 4};  // patch width per level kind {proposal, NeRF}: 0 = rows of 32 pixels, 4 / 8 / 16 = 4x8 / 8x4 / 16x2
     int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 FP16 split (error if shapes unsupported), 2 = auto
     bool use_affine = false;
     float affine[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};   // BrightnessCorrection affine of the current image (row-major 3x4)
@@ -368,7 +369,9 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         std::memcpy(sp.g2, ls.g2, sizeof(sp.g2));
         sp.cell_runs = (m->encode_runs >> (nerf ? 1 : 0)) & 1;
         sp.mlp_mma = (m->encode_mlp_mma >> (nerf ? 1 : 0)) & 1;
-        sp.tile_w = (tile_w > 0 && ray0 % (size_t)tile_w == 0) ? (uint32_t)tile_w : 0u;
+        const int patch = m->ray_tile_patch[nerf ? 1 : 0];
+        sp.tile_w = (patch > 0 && tile_w > 0 && tile_w % (uint64_t)patch == 0 && ray0 % (size_t)tile_w == 0) ? (uint32_t)tile_w : 0u;
+        sp.tile_pw_log2 = patch == 16 ? 4u : patch == 8 ? 3u : 2u;
         sp.rw_log2 = m->warp_rays_log2[nerf ? 1 : 0];
         if (S % (32 >> sp.rw_log2) != 0) sp.rw_log2 = 5;   // sample blocks must tile S
         float* rgb_s = nullptr;
@@ -492,6 +495,10 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
     UC_REQUIRE(m && key, "set_option: null argument");
     const std::string k(key);
     if (k == "chunk_rays") { UC_REQUIRE(value >= 1, "chunk_rays must be >= 1"); m->chunk_rays = value; }
+    else if (k == "ray_tile_prop" || k == "ray_tile_nerf") {
+        UC_REQUIRE(value == 0 || value == 4 || value == 8 || value == 16, "ray_tile_*: patch width 0 (rows), 4, 8 or 16");
+        m->ray_tile_patch[k == "ray_tile_nerf" ? 1 : 0] = (int)value;
+    }
     else if (k == "ray_tile_width") {
         UC_REQUIRE(value >= 0 && value % 4 == 0 && value <= (1 << 20), "ray_tile_width: image width, a multiple of 4 (0 = off)");
         m->ray_tile_width = value;

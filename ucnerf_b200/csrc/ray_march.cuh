@@ -48,7 +48,9 @@ struct SampleParams {
     int rw_log2;             // warp shape of sample_encode_kernel: 2^rw_log2 rays x 2^(5 - rw_log2) samples (5 = 32 rays x 1)
     int cell_runs;           // 1: level-outer loop with cell-run reuse of the gathered corners (sample_encode.cu)
     uint32_t tile_w;         // > 0: the rays of this launch are whole rows of an image of this width (row-major): a warp of
-                             // sample_encode_kernel then takes a 4 x 8 pixel patch instead of 32 pixels of one row
+                             // sample_encode_kernel then takes a patch of 2^tile_pw_log2 x 32 / 2^tile_pw_log2 pixels
+                             // instead of 32 pixels of one row
+    uint32_t tile_pw_log2;   // 2, 3 or 4 (patch 4 x 8, 8 x 4, 16 x 2)
     int mlp_mma;             // 1: density layer on the tensor cores (mma.sync 3xTF32), 0: FFMA2 forms (sample_encode.cu)
 };
 

@@ -137,20 +137,21 @@ struct SamplePos {
 // rays x 2^(5 - rw_log2) consecutive samples; the warps of a group enumerate (sample block, ray block).
 //
 // tile_w > 0 (the rays are whole rows of a row-major image of that width, SampleParams::tile_w): the 32 rays of a group
-// are a patch of 4 x 8 pixels (lane -> dx = lane % 4, dy = lane / 4) instead of 32 pixels of one row.  Same rays, same
+// are a patch of pw x 32 / pw pixels (lane -> dx = lane % pw, dy = lane / pw; pw = 4, 8 or 16) instead of 32 pixels of one row.  Same rays, same
 // results, another assignment of rays to warps: the lanes of a gather are closer together in the scene, so they share
 // more cells and 128-byte lines on the middle levels (measured with permuted ray batches in round 1:
 // profiles/r1_summary.md; here without moving any data).  Bands of 8 rows that do not fit keep the row mapping.
 struct BlockSamples {
-    uint32_t group, rem0, span, n_rays, tile_w, tiles_per_band, tiled_groups;
+    uint32_t group, rem0, span, n_rays, tile_w, pw_log2, tiles_per_band, tiled_groups;
     int S, rw_log2;
-    __device__ __forceinline__ BlockSamples(size_t block0, uint32_t n_rays_, int S_, int rw_log2_, uint32_t tile_w_)
-        : span(32u * (uint32_t)S_), n_rays(n_rays_), tile_w(rw_log2_ == 5 ? tile_w_ : 0u), S(S_), rw_log2(rw_log2_) {
+    __device__ __forceinline__ BlockSamples(size_t block0, uint32_t n_rays_, int S_, int rw_log2_, uint32_t tile_w_, uint32_t pw_log2_)
+        : span(32u * (uint32_t)S_), n_rays(n_rays_), tile_w(rw_log2_ == 5 ? tile_w_ : 0u), pw_log2(pw_log2_), S(S_), rw_log2(rw_log2_) {
         const size_t g = block0 / span;
         group = (uint32_t)g;
         rem0 = (uint32_t)(block0 - g * span);
-        tiles_per_band = tile_w >> 2;
-        tiled_groups = tile_w ? (n_rays / (8u * tile_w)) * tiles_per_band : 0u;
+        tiles_per_band = tile_w >> pw_log2;
+        const uint32_t band_rays = (32u >> pw_log2) * tile_w;       // rows of a band x width
+        tiled_groups = tile_w ? (n_rays / band_rays) * tiles_per_band : 0u;
     }
     __device__ __forceinline__ SamplePos at(uint32_t i) const {
         uint32_t rem = rem0 + i, grp = group;
@@ -160,7 +161,7 @@ struct BlockSamples {
         SamplePos sp;
         if (grp < tiled_groups) {
             const uint32_t band = grp / tiles_per_band, col = grp - band * tiles_per_band;
-            sp.ray = (8u * band + (lane >> 2)) * tile_w + 4u * col + (lane & 3u);
+            sp.ray = ((32u >> pw_log2) * band + (lane >> pw_log2)) * tile_w + (col << pw_log2) + (lane & ((1u << pw_log2) - 1u));
         } else {
             sp.ray = grp * 32u + (ray_block << rw_log2) + (lane & ((1u << rw_log2) - 1u));
         }
@@ -248,7 +249,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
 
     if constexpr (MMA) __syncthreads();  // weights staged; the warps run independently from here on
     const size_t block0 = (size_t)blockIdx.x * kSampleThreads;
-    const BlockSamples samples(block0, p.n_rays, p.S, p.rw_log2, p.tile_w);
+    const BlockSamples samples(block0, p.n_rays, p.S, p.rw_log2, p.tile_w, p.tile_pw_log2);
     const SamplePos me = samples.at(threadIdx.x);
     const size_t idx = (size_t)me.ray * p.S + me.s;  // row of this sample in the [N*S] buffers
     float2 F2[LMAX * 2];  // pooled features, (x,y) / (z,w) pairs per level

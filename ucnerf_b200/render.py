@@ -568,13 +568,22 @@ def render_image(model, accelerator, batch, rand, train_frac, config, verbose=Tr
     # sky head still has to blend into the pixels afterwards or `config.ucnerf_peer_exchange = False`
     peer = _peer_image(r, world, per, config) if (world > 1 and not use_sky) else None
     peer_img = None
+    # this rank's tile is a run of whole image rows when it starts on a row: tell the library the row length, so that the
+    # gather kernel's warps take pixel patches instead of 32 pixels of one row (bit-identical, see ray_tile_width)
+    tiled = width % 4 == 0 and start % width == 0 and hasattr(r, "set_option")
     try:
+        if tiled:
+            r.set_option("ray_tile_width", width)
         if peer is not None:
             peer_img, out = peer.render(r, local, train_frac, lrv, rank * per, [w for w in want if w != "packed"])
         else:
             out = r.render_rays(local, train_frac, lrv, want)
+        if tiled:
+            r.set_option("ray_tile_width", 0)     # the picked rays below are no image
         vis = r.render_rays({k: v[pick] for k, v in local.items()}, train_frac, lrv[pick], vis_want)
     finally:
+        if tiled:
+            r.set_option("ray_tile_width", 0)
         if affine is not None:
             r.set_rgb_affine(None)   # the affine belongs to this image only, also when the render raises
     packed = out["packed"] if peer_img is None else None

@@ -293,7 +293,11 @@ uint64_t ucnerf_launch_count(void);
  * tensor cores whenever the MLP widths allow, the default), "timing" (see ucnerf_get_timing), "encode_mlp_mma" (density
  * layer of the sample/encode kernel as mma.sync 3xTF32: bit 0 = proposal levels, bit 1 = NeRF level, default 3; 0 = the
  * fp32 FMA forms), "encode_runs" (cell-run reuse of gathered corners, bit-identical, default 0; implies the FMA forms),
- * "warp_rays_prop" / "warp_rays_nerf" (rays per warp of that kernel: 32, 16, 8 or 4). */
+ * "warp_rays_prop" / "warp_rays_nerf" (rays per warp of that kernel: 32, 16, 8 or 4), "ray_tile_width" (W > 0, a multiple of
+ * 4: the ray batches of ucnerf_render_rays[_host] are whole rows of a row-major image W pixels wide, so the warps of that
+ * kernel may take pixel patches instead of 32 pixels of one row - results are bit-identical for ANY batch, the hint only
+ * changes which rays share a warp; the camera entries know W and do this by themselves; 0 = off, the default),
+ * "ray_tile_prop" / "ray_tile_nerf" (patch width per level kind: 0 = rows, 4 = 4x8, 8 = 8x4, 16 = 16x2; default 0 / 4). */
 int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value);
 
 /* Brightness-correction head folded into the compositing epilogue.  The reference evaluates

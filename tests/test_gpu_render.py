@@ -134,6 +134,21 @@ def test_image_patch_warp_mapping_is_bit_identical(width, n, shapes):
         assert np.array_equal(got[k], ref[k]), k
 
 
+def test_per_ray_cone_basis_precompute_is_bit_identical():
+    """Option ray_geom: the cone basis of a ray (two cross products + normalisations) from ray_geom_kernel, once per ray,
+    instead of per sample inside the encode kernel - the same arithmetic, so the same bits."""
+    cfg, params, _, r = case("waymo")
+    batch = O.synthetic_rays(4099, seed=45)
+    try:
+        r.set_option("ray_geom", 0)
+        ref = run(r, batch)
+    finally:
+        r.set_option("ray_geom", 1)
+    got = run(r, batch)
+    for k in ("rgb", "acc", "depth", "sample_density", "sample_rgb", "weights_0", "weights_1", "sdist_1"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
 def test_host_entry_equals_device_entry():
     """ucnerf_render_rays_host (H2D + render + D2H inside the call) returns exactly the device-entry results."""
     cfg, params, batch, r = case("waymo")

@@ -73,14 +73,15 @@ struct ucnerf_model {
     uint32_t tc_debug = 0;
     float tc_k0 = 1.f, tc_k1 = 1.f;   // accumulator scales of the FP16-split tensor-core colour MLP
     bool tc_ok = false;   // tensor-core colour MLP available for these shapes (W = 256, deg_view = 4)
-    DevBuf density, h1, rgb_s;
+    DevBuf density, h1, rgb_s, geom;
     // host-entry staging
     DevBuf stage_in, stage_out, cam_rays;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host entry: H2D / D2H overlap the render stream chunk by chunk
     std::vector<cudaEvent_t> ev_in, ev_done;
     int64_t chunk_rays = 131072;
     int64_t ray_tile_width = 0;  // > 0: ray batches are whole rows of a row-major image of this width (see SampleParams::tile_w)
-    int ray_tile_patch[2] = {0, 4};  // patch width per level kind {proposal, NeRF}: 0 = rows of 32 pixels, 4 / 8 / 16 = 4x8 / 8x4 / 16x2
+    int ray_tile_patch[2] = {0, 4};
+    int ray_geom = 1;  // per-ray cone basis precomputed once per chunk (ray_geom_kernel) instead of per sample  // patch width per level kind {proposal, NeRF}: 0 = rows of 32 pixels, 4 / 8 / 16 = 4x8 / 8x4 / 16x2
     int color_mode = 2;   // 0 = fp32 SIMT, 1 = tcgen05 FP16 split (error if shapes unsupported), 2 = auto
     bool use_affine = false;
     float affine[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};   // BrightnessCorrection affine of the current image (row-major 3x4)
@@ -321,6 +322,14 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
     int smax = 0;
     for (int li = 0; li < m->num_levels; ++li) smax = std::max(smax, m->lv[li].S);
     if (int e = m->density.ensure((size_t)n * smax * sizeof(float))) return e;
+    // the cone basis of every ray of the chunk, once (all levels and samples read it)
+    const uint32_t geom_ld = (n + 31u) & ~31u;
+    const float* geom = nullptr;
+    if (m->ray_geom) {
+        if (int e = m->geom.ensure((size_t)15 * geom_ld * sizeof(float))) return e;
+        if (int e = launch_ray_geom(rp, n, m->geom.as<float>(), geom_ld, st)) return e;
+        geom = m->geom.as<float>();
+    }
 
     const float* t_prev = nullptr;
     const float* w_prev = nullptr;
@@ -369,6 +378,7 @@ static int render_chunk(ucnerf_model* m, uint32_t n, const ucnerf_rays& r, size_
         std::memcpy(sp.g2, ls.g2, sizeof(sp.g2));
         sp.cell_runs = (m->encode_runs >> (nerf ? 1 : 0)) & 1;
         sp.mlp_mma = (m->encode_mlp_mma >> (nerf ? 1 : 0)) & 1;
+        sp.geom = geom; sp.geom_ld = geom_ld;
         const int patch = m->ray_tile_patch[nerf ? 1 : 0];
         sp.tile_w = (patch > 0 && tile_w > 0 && tile_w % (uint64_t)patch == 0 && ray0 % (size_t)tile_w == 0) ? (uint32_t)tile_w : 0u;
         sp.tile_pw_log2 = patch == 16 ? 4u : patch == 8 ? 3u : 2u;
@@ -495,6 +505,7 @@ extern "C" int ucnerf_set_option(ucnerf_model* m, const char* key, int64_t value
     UC_REQUIRE(m && key, "set_option: null argument");
     const std::string k(key);
     if (k == "chunk_rays") { UC_REQUIRE(value >= 1, "chunk_rays must be >= 1"); m->chunk_rays = value; }
+    else if (k == "ray_geom") m->ray_geom = value != 0;
     else if (k == "ray_tile_prop" || k == "ray_tile_nerf") {
         UC_REQUIRE(value == 0 || value == 4 || value == 8 || value == 16, "ray_tile_*: patch width 0 (rows), 4, 8 or 16");
         m->ray_tile_patch[k == "ray_tile_nerf" ? 1 : 0] = (int)value;

@@ -52,6 +52,8 @@ struct SampleParams {
                              // instead of 32 pixels of one row
     uint32_t tile_pw_log2;   // 2, 3 or 4 (patch 4 x 8, 8 x 4, 16 x 2)
     int mlp_mma;             // 1: density layer on the tensor cores (mma.sync 3xTF32), 0: FFMA2 forms (sample_encode.cu)
+    const float* geom;       // [15][geom_ld] per-ray RayGeom (o, d, e1, e2, radius, near, far) from ray_geom_kernel, or NULL:
+    uint32_t geom_ld;        // every sample of a ray needs the same basis - built once per ray, read coalesced
 };
 
 // Colour MLP with the linear bottleneck layer folded into its two consumers (exact algebra, see model.cu):
@@ -159,6 +161,7 @@ int sky_tc_steps();
 float sky_tc_act_scale();
 void sky_tc_pack_chunk(const float* wt_rows, int n_cols, float scale, uint8_t* dst);
 int sample_encode_lmax(int L);
+int launch_ray_geom(const RayPtrs& rays, uint32_t n_rays, float* geom, uint32_t geom_ld, cudaStream_t st);
 // h1 column c holds hidden unit h1_perm(c) of density_layer.0 (layout written by sample_encode_kernel): lane t of a
 // quad owns the accumulator columns {8 nt + 2 t + e} of the mma.sync C fragments.  They are stored as two 32-byte pieces
 // (nt < 4 / nt >= 4) at columns 32 (nt / 4) + 8 t + 2 (nt % 4) + e, so that one 256-bit store instruction of a quad covers

@@ -171,6 +171,55 @@ struct BlockSamples {
     }
 };
 
+// The basis of a ray's cones (render.py:L139-146: two cross products and normalisations) is the same for all its samples:
+// ray_geom_kernel evaluates make_ray_geom once per ray into a [15][ld] array that the sample threads read coalesced
+// (same arithmetic, same bits; 15 strided loads and about 100 instructions less per sample).
+__global__ void __launch_bounds__(256) ray_geom_kernel(RayPtrs r, uint32_t n_rays, float* __restrict__ geom, uint32_t ld) {
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    RayGeom g;
+    make_ray_geom(g, r.origins + 3 * (size_t)ray, r.directions + 3 * (size_t)ray, r.cam_dirs + 3 * (size_t)ray,
+                  r.rand_vec + 3 * (size_t)ray, r.radii[ray], r.near[ray], r.far[ray]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        geom[(size_t)i * ld + ray] = g.o[i];
+        geom[(size_t)(3 + i) * ld + ray] = g.d[i];
+        geom[(size_t)(6 + i) * ld + ray] = g.e1[i];
+        geom[(size_t)(9 + i) * ld + ray] = g.e2[i];
+    }
+    geom[(size_t)12 * ld + ray] = g.radius;
+    geom[(size_t)13 * ld + ray] = g.near;
+    geom[(size_t)14 * ld + ray] = g.far;
+}
+
+int launch_ray_geom(const RayPtrs& rays, uint32_t n_rays, float* geom, uint32_t geom_ld, cudaStream_t st) {
+    if (n_rays == 0) return 0;
+    ray_geom_kernel<<<div_up(n_rays, 256u), 256, 0, st>>>(rays, n_rays, geom, geom_ld);
+    UC_LAUNCH_CHECK();
+    return 0;
+}
+
+__device__ __forceinline__ void load_ray_geom(RayGeom& rg, const SampleParams& p, uint32_t ray) {
+    if (p.geom) {
+        const float* g = p.geom + ray;
+        const size_t ld = p.geom_ld;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            rg.o[i] = g[(size_t)i * ld];
+            rg.d[i] = g[(size_t)(3 + i) * ld];
+            rg.e1[i] = g[(size_t)(6 + i) * ld];
+            rg.e2[i] = g[(size_t)(9 + i) * ld];
+        }
+        rg.radius = g[(size_t)12 * ld];
+        rg.near = g[(size_t)13 * ld];
+        rg.far = g[(size_t)14 * ld];
+    } else {
+        make_ray_geom(rg, p.rays.origins + 3 * (size_t)ray, p.rays.directions + 3 * (size_t)ray,
+                      p.rays.cam_dirs + 3 * (size_t)ray, p.rays.rand_vec + 3 * (size_t)ray, p.rays.radii[ray],
+                      p.rays.near[ray], p.rays.far[ray]);
+    }
+}
+
 // ND >= 0: levels [0, ND) are dense, levels >= ND hashed with power-of-two tables (compile-time specialisation);
 // ND < 0: decide per level at run time.
 //
@@ -266,9 +315,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
             uint32_t inmask = 0;
             {
                 RayGeom rg;
-                make_ray_geom(rg, p.rays.origins + 3 * (size_t)ray, p.rays.directions + 3 * (size_t)ray,
-                              p.rays.cam_dirs + 3 * (size_t)ray, p.rays.rand_vec + 3 * (size_t)ray, p.rays.radii[ray],
-                              p.rays.near[ray], p.rays.far[ray]);
+                load_ray_geom(rg, p, ray);
                 const float s0 = p.sdist[(size_t)ray * p.sdist_stride + s];
                 const float s1 = p.sdist[(size_t)ray * p.sdist_stride + s + 1];
                 const float t0 = fa(fm(s0, rg.far), fm(fs(1.f, s0), rg.near));
@@ -331,9 +378,7 @@ sample_encode_kernel(const __grid_constant__ SampleParams p) {
         const uint32_t ray = me.ray;
         const int s = me.s;
         RayGeom rg;
-        make_ray_geom(rg, p.rays.origins + 3 * (size_t)ray, p.rays.directions + 3 * (size_t)ray,
-                      p.rays.cam_dirs + 3 * (size_t)ray, p.rays.rand_vec + 3 * (size_t)ray, p.rays.radii[ray],
-                      p.rays.near[ray], p.rays.far[ray]);
+        load_ray_geom(rg, p, ray);
         const float s0 = p.sdist[(size_t)ray * p.sdist_stride + s];
         const float s1 = p.sdist[(size_t)ray * p.sdist_stride + s + 1];
         const float t0 = fa(fm(s0, rg.far), fm(fs(1.f, s0), rg.near));

@@ -5,9 +5,10 @@ bytes (dram__bytes_read.sum + dram__bytes_write.sum), the launch duration under 
 
     gpurun -- 'ncu --set full --clock-control none --import-source on -k regex:"sample_encode|color_mlp_tc|resample_kernel|composite_kernel" \
                -c 10 -o gpurun_out/r2_full python bench.py --extras none --steps 1 --warmup 1'
-    python tools/ncu_traffic.py gpurun_out/r2_full.ncu-rep [build tag]
+    python tools/ncu_traffic.py gpurun_out/r2_full.ncu-rep [build tag] [rays per chunk]
 
-The first launch of every family is the first 131,072-ray chunk of the eval_800x600_waymo_gin frame."""
+The first launch of every family is the first chunk of the eval_800x600_waymo_gin frame: 131,072 rays, or - with bench.py's
+default ray_tile_width = 800 - 128,000 (a whole number of 8-row bands)."""
 import csv
 import io
 import json
@@ -58,10 +59,11 @@ def main():
         u = units[hits[0]]
         return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "us": 1e-3, "ms": 1, "ns": 1e-6, "s": 1e3}.get(u, 1)
 
+    chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 131072
     out = {"_comment": f"per-launch numbers from `ncu --set full --clock-control none` ({os.path.basename(rep)}, build {tag}): first "
-                       "131,072-ray chunk of eval_800x600_waymo_gin; written by tools/ncu_traffic.py; bench.py copies them into "
+                       f"{chunk:,}-ray chunk of eval_800x600_waymo_gin; written by tools/ncu_traffic.py; bench.py copies them into "
                        "roofline.traffic / dram_frac / bound",
-           "workload": "eval_800x600_waymo_gin", "chunk_rays": 131072, "build": tag}
+           "workload": "eval_800x600_waymo_gin", "chunk_rays": chunk, "build": tag}
     # per family the longest launch of the capture (e.g. the level-1 resample, not the trivial level-0 one)
     body = sorted(rows[2:], key=lambda r: -(val(r, "gpu__time_duration.sum") or 0))
     for r in body:
